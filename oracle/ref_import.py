@@ -1,0 +1,88 @@
+"""TEST INFRASTRUCTURE ONLY - imports the *real* reference modules from /root/reference.
+
+Only usable in the authoring container (``/root/reference`` does not exist on the
+GPU box).  Used by ``oracle/gen_golden.py`` to produce the fixtures under
+``tests/golden/`` and by CPU tests that pin ``oracle/seedvc_oracle.py`` to the
+reference directly when the tree is present.
+
+The reference imports three packages that are not installed here and that the
+hot path never calls: ``munch`` (modules/commons.py:6),
+``matplotlib`` (modules/bigvgan/utils.py:7-11) and ``librosa``
+(modules/bigvgan/meldataset.py:13-15).  Tiny stand-ins are put in
+``sys.modules`` before importing.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("SEEDVC_REFERENCE", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "modules"))
+
+
+def _install_stubs():
+    if "munch" not in sys.modules:
+        m = types.ModuleType("munch")
+
+        class Munch(dict):
+            def __getattr__(self, k):
+                try:
+                    return self[k]
+                except KeyError as e:
+                    raise AttributeError(k) from e
+
+            def __setattr__(self, k, v):
+                self[k] = v
+
+        m.Munch = Munch
+        sys.modules["munch"] = m
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib")
+        mpl.use = lambda *a, **k: None
+        pylab = types.ModuleType("matplotlib.pylab")
+        pyplot = types.ModuleType("matplotlib.pyplot")
+        mpl.pylab, mpl.pyplot = pylab, pyplot
+        sys.modules.update({"matplotlib": mpl, "matplotlib.pylab": pylab,
+                            "matplotlib.pyplot": pyplot})
+    if "librosa" not in sys.modules:
+        lb = types.ModuleType("librosa")
+        util = types.ModuleType("librosa.util")
+        util.normalize = lambda x, *a, **k: x
+        filters = types.ModuleType("librosa.filters")
+        filters.mel = lambda *a, **k: None
+        lb.util, lb.filters = util, filters
+        sys.modules.update({"librosa": lb, "librosa.util": util,
+                            "librosa.filters": filters})
+
+
+def load():
+    """Return a namespace with the reference classes of the hot path."""
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    _install_stubs()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    import warnings
+
+    warnings.filterwarnings("ignore", category=FutureWarning)
+    warnings.filterwarnings("ignore", category=UserWarning)
+    from modules.flow_matching import CFM  # noqa: E402
+    from modules.diffusion_transformer import DiT  # noqa: E402
+    from modules.bigvgan.bigvgan import BigVGAN  # noqa: E402
+    from modules.bigvgan.env import AttrDict as BigVGANAttrDict  # noqa: E402
+    from modules.bigvgan.alias_free_activation.torch.act import Activation1d  # noqa: E402
+    from modules.bigvgan.activations import SnakeBeta, Snake  # noqa: E402
+    from modules.v2.cfm import CFM as CFMv2  # noqa: E402
+    from modules.v2.dit_wrapper import DiT as DiTv2  # noqa: E402
+    from modules.wavenet import WN  # noqa: E402
+
+    ns = types.SimpleNamespace(
+        CFM=CFM, DiT=DiT, BigVGAN=BigVGAN, BigVGANAttrDict=BigVGANAttrDict,
+        Activation1d=Activation1d, SnakeBeta=SnakeBeta, Snake=Snake,
+        CFMv2=CFMv2, DiTv2=DiTv2, WN=WN,
+    )
+    return ns

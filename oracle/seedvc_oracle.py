@@ -1,0 +1,405 @@
+"""TEST INFRASTRUCTURE ONLY - CPU restatement of the Seed-VC conversion hot path.
+
+This file is the *oracle*: a plain fp32 PyTorch-on-CPU restatement of the
+reference algorithm, written from the reference's maths (each function cites the
+reference file:line it follows).  It must never be imported by the product
+package ``seed-vc_b200``; only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may use it, as the
+checker or as the timed CPU baseline.
+
+Parity pin: the reference ships no tests or golden vectors for this path
+(SURVEY.md section 4), so the oracle is pinned against outputs of the reference
+itself, generated in the authoring container by ``oracle/gen_golden.py``
+(which imports /root/reference) and committed under ``tests/golden/``.
+``tests/test_oracle_golden.py`` checks every fixture.
+
+All functions take a flat ``state_dict`` with the reference's parameter names.
+Batched semantics: the reference's CFG path only runs at batch 1
+(SURVEY.md App. D-1); a batch here is *defined* as the per-utterance batch-1
+result, each utterance using its own ``x_lens[b]`` as its whole length.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------
+# small helpers
+# ----------------------------------------------------------------------------
+def _wn_weight(sd, prefix):
+    """w = g * v / ||v||, norm over all dims but 0 (torch weight_norm dim=0;
+    reference: modules/diffusion_transformer.py:395,431, modules/wavenet.py:120-135)."""
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"]
+    v, g = sd[prefix + ".weight_v"], sd[prefix + ".weight_g"]
+    n = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+    return g * v / n
+
+
+def _linear(sd, prefix, x):
+    return F.linear(x, _wn_weight(sd, prefix), sd.get(prefix + ".bias"))
+
+
+def rmsnorm(x, w, eps=1e-5):
+    """modules/diffusion_transformer.py:274-285"""
+    return x * torch.rsqrt(torch.mean(x * x, dim=-1, keepdim=True) + eps) * w
+
+
+def timestep_embedding(t, dim=256, max_period=10000.0, scale=1000.0):
+    """modules/diffusion_transformer.py:341-359 (v2: modules/v2/dit_wrapper.py:32-50)"""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    args = scale * t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def t_embedder(sd, prefix, t):
+    """modules/diffusion_transformer.py:361-364"""
+    h = _linear(sd, prefix + ".mlp.0", timestep_embedding(t))
+    return _linear(sd, prefix + ".mlp.2", F.silu(h))
+
+
+def rope_table(n_pos, head_dim=64, base=10000.0, bf16_round=False):
+    """modules/diffusion_transformer.py:288-297.  v2 stores the table in bf16
+    (modules/v2/dit_model.py:100-101,225-234)."""
+    freqs = 1.0 / (base ** (torch.arange(0, head_dim, 2)[: head_dim // 2].float() / head_dim))
+    ang = torch.outer(torch.arange(n_pos), freqs)
+    tab = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1)
+    if bf16_round:
+        tab = tab.to(torch.bfloat16).float()
+    return tab  # (n_pos, hd/2, 2)
+
+
+def apply_rope(x, tab):
+    """Interleaved-pair rotation, modules/diffusion_transformer.py:300-312. x: (B,T,H,hd)."""
+    xs = x.float().reshape(*x.shape[:-1], -1, 2)
+    c = tab[None, : x.shape[1], None, :, 0]
+    s = tab[None, : x.shape[1], None, :, 1]
+    out = torch.stack([xs[..., 0] * c - xs[..., 1] * s, xs[..., 1] * c + xs[..., 0] * s], -1)
+    return out.flatten(3)
+
+
+def attention(sd, prefix, x, tab, n_head, kv_len):
+    """modules/diffusion_transformer.py:222-260: wqkv, RoPE, masked SDPA, wo."""
+    B, T, D = x.shape
+    hd = D // n_head
+    q, k, v = F.linear(x, sd[prefix + ".wqkv.weight"]).split([D, D, D], dim=-1)
+    q = apply_rope(q.view(B, T, n_head, hd), tab).transpose(1, 2)
+    k = apply_rope(k.view(B, T, n_head, hd), tab).transpose(1, 2)
+    v = v.view(B, T, n_head, hd).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    key_ok = torch.arange(T)[None, :] < kv_len[:, None]            # (B, T)
+    s = s.masked_fill(~key_ok[:, None, None, :], float("-inf"))
+    y = torch.softmax(s, dim=-1) @ v
+    y = y.transpose(1, 2).reshape(B, T, D)
+    return F.linear(y, sd[prefix + ".wo.weight"])
+
+
+def feed_forward(sd, prefix, x):
+    """modules/diffusion_transformer.py:263-271"""
+    return F.linear(F.silu(F.linear(x, sd[prefix + ".w1.weight"])) *
+                    F.linear(x, sd[prefix + ".w3.weight"]), sd[prefix + ".w2.weight"])
+
+
+def adaln_v1(sd, prefix, x, c):
+    """modules/diffusion_transformer.py:30-48: w*RMSNorm(x)+b, no SiLU, no '1+'."""
+    n = rmsnorm(x, sd[prefix + ".norm.weight"])
+    if c is None:
+        return n
+    D = x.shape[-1]
+    w, b = torch.split(_linear(sd, prefix + ".project_layer", c), D, dim=-1)
+    return w * n + b
+
+
+# ----------------------------------------------------------------------------
+# v1 estimator
+# ----------------------------------------------------------------------------
+def wavenet(sd, prefix, x, g, n_layers, hidden):
+    """modules/wavenet.py:138-166 with SConv1d reflect padding
+    (modules/encodec.py:212-228; the conv's own padding kwarg is swallowed,
+    SURVEY section 8 a8).  x: (B, Dw, T); g: (B, Dw, 1); mask is all ones at
+    batch-1 semantics."""
+    out = torch.zeros_like(x)
+    g = F.conv1d(g, _wn_weight(sd, prefix + ".cond_layer.conv.conv"),
+                 sd[prefix + ".cond_layer.conv.conv.bias"])
+    for i in range(n_layers):
+        w = _wn_weight(sd, f"{prefix}.in_layers.{i}.conv.conv")
+        k = w.shape[-1]
+        pad_total = k - 1
+        pr = pad_total // 2
+        pl = pad_total - pr
+        x_in = F.conv1d(F.pad(x, (pl, pr), mode="reflect"), w,
+                        sd[f"{prefix}.in_layers.{i}.conv.conv.bias"])
+        a = x_in + g[:, i * 2 * hidden:(i + 1) * 2 * hidden]
+        acts = torch.tanh(a[:, :hidden]) * torch.sigmoid(a[:, hidden:])   # commons.py:131-138
+        rs = F.conv1d(acts, _wn_weight(sd, f"{prefix}.res_skip_layers.{i}.conv.conv"),
+                      sd[f"{prefix}.res_skip_layers.{i}.conv.conv.bias"])
+        if i < n_layers - 1:
+            x = x + rs[:, :hidden]
+            out = out + rs[:, hidden:]
+        else:
+            out = out + rs
+    return out
+
+
+def dit_v1_forward(sd, args, x, prompt_x, x_lens, t, style, cond, pfx="estimator."):
+    """modules/diffusion_transformer.py:486-537 (inference branch).
+
+    x, prompt_x: (N, C, T); t: (N,); style: (N, 192); cond: (N, T, content_dim).
+    Every row uses its own full length T (batch-1 semantics)."""
+    dit = args.DiT
+    D, H, L, C = dit.hidden_dim, dit.num_heads, dit.depth, dit.in_channels
+    tat = bool(getattr(dit, "time_as_token", False))
+    sat = bool(getattr(dit, "style_as_token", False))
+    uvit = bool(getattr(dit, "uvit_skip_connection", False))
+    N, _, T = x.shape
+    t1 = t_embedder(sd, pfx + "t_embedder", t)
+    cond = _linear(sd, pfx + "cond_projection", cond)
+    xt = x.transpose(1, 2)
+    x_in = torch.cat([xt, prompt_x.transpose(1, 2), cond], dim=-1)
+    if dit.style_condition and not sat:
+        x_in = torch.cat([x_in, style[:, None, :].repeat(1, T, 1)], dim=-1)
+    h = _linear(sd, pfx + "cond_x_merge_linear", x_in)
+    if sat:
+        h = torch.cat([_linear(sd, pfx + "style_in", style).unsqueeze(1), h], dim=1)
+    if tat:
+        h = torch.cat([t1.unsqueeze(1), h], dim=1)
+    ntok = int(tat) + int(sat)
+    Tq = T + ntok
+    kv_len = x_lens + ntok
+    tab = rope_table(Tq)
+    c = t1.unsqueeze(1)
+    c_layer = None if tat else c                                     # :184
+    emit = [i for i in range(L) if i < L // 2] if uvit else []
+    recv = [i for i in range(L) if i > L // 2] if uvit else []
+    skips = []
+    for i in range(L):
+        lp = f"{pfx}transformer.layers.{i}"
+        if i in recv:
+            h = _linear(sd, lp + ".skip_in_linear", torch.cat([h, skips.pop(-1)], dim=-1))
+        h = h + attention(sd, lp + ".attention", adaln_v1(sd, lp + ".attention_norm", h, c_layer),
+                          tab, H, kv_len)
+        h = h + feed_forward(sd, lp + ".feed_forward", adaln_v1(sd, lp + ".ffn_norm", h, c_layer))
+        if i in emit:
+            skips.append(h)
+    h = adaln_v1(sd, pfx + "transformer.norm", h, c)                 # :142 uses c even with tokens
+    h = h[:, ntok:]
+    if dit.long_skip_connection:
+        h = _linear(sd, pfx + "skip_linear", torch.cat([h, xt], dim=-1))
+    if dit.final_layer_type == "wavenet":
+        Dw = args.wavenet.hidden_dim
+        y = _linear(sd, pfx + "conv1", h).transpose(1, 2)
+        t2 = t_embedder(sd, pfx + "t_embedder2", t)
+        y = wavenet(sd, pfx + "wavenet", y, t2.unsqueeze(2), args.wavenet.num_layers, Dw)
+        y = y.transpose(1, 2) + _linear(sd, pfx + "res_projection", h)
+        mod = _linear(sd, pfx + "final_layer.adaLN_modulation.1", F.silu(t1))   # :401-405
+        shift, scale = mod.chunk(2, dim=1)
+        y = F.layer_norm(y, (Dw,), eps=1e-6) * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+        y = _linear(sd, pfx + "final_layer.linear", y).transpose(1, 2)
+        return F.conv1d(y, sd[pfx + "conv2.weight"], sd[pfx + "conv2.bias"])
+    y = _linear(sd, pfx + "final_mlp.2", F.silu(_linear(sd, pfx + "final_mlp.0", h)))
+    return y.transpose(1, 2)
+
+
+def solve_euler_v1(sd, args, z, x_lens, prompt, mu, style, t_span, cfg_rate, return_steps=False):
+    """modules/flow_matching.py:55-112, applied per utterance (batch-1 semantics).
+
+    z: (B, C, T) injected noise; prompt: (B, C, Tp); mu: (B, T, content_dim);
+    style: (B, 192).  Returns (B, C, T) with rows t >= x_lens[b] zeroed."""
+    B, C, T = z.shape
+    outs, steps = [], []
+    for b in range(B):
+        Tb = int(x_lens[b])
+        x = z[b:b + 1, :, :Tb].clone()
+        Tp = min(prompt.shape[-1], Tb)
+        prompt_x = torch.zeros_like(x)
+        prompt_x[..., :Tp] = prompt[b:b + 1, :, :Tp]
+        x[..., :Tp] = 0
+        m = mu[b:b + 1, :Tb]
+        s = style[b:b + 1]
+        xl = torch.tensor([Tb])
+        t = t_span[0]
+        vs = []
+        for step in range(1, len(t_span)):
+            dt = t_span[step] - t_span[step - 1]
+            if cfg_rate > 0:
+                v2 = dit_v1_forward(
+                    sd, args, torch.cat([x, x]), torch.cat([prompt_x, torch.zeros_like(prompt_x)]),
+                    xl, torch.stack([t, t]), torch.cat([s, torch.zeros_like(s)]),
+                    torch.cat([m, torch.zeros_like(m)]))
+                v = (1.0 + cfg_rate) * v2[0:1] - cfg_rate * v2[1:2]
+            else:
+                v = dit_v1_forward(sd, args, x, prompt_x, xl, t.unsqueeze(0), s, m)
+            vs.append(v)
+            x = x + dt * v
+            t = t + dt
+            x[:, :, :Tp] = 0
+        outs.append(F.pad(x, (0, T - Tb)))
+        steps.append(vs)
+    out = torch.cat(outs)
+    return (out, steps) if return_steps else out
+
+
+# ----------------------------------------------------------------------------
+# v2 estimator and sampler
+# ----------------------------------------------------------------------------
+def dit_v2_forward(sd, kw, x, prompt_x, x_lens, t, style, cond, pfx=""):
+    """modules/v2/dit_wrapper.py:114-152 + modules/v2/dit_model.py:109-143."""
+    D, H, L, C = kw["hidden_dim"], kw["num_heads"], kw["depth"], kw["in_channels"]
+    tat, sat = bool(kw["time_as_token"]), bool(kw["style_as_token"])
+    N, _, T = x.shape
+    t1 = t_embedder(sd, pfx + "t_embedder", t)
+    cond = _linear(sd, pfx + "cond_projection", cond)
+    x_in = torch.cat([x.transpose(1, 2), prompt_x.transpose(1, 2), cond], dim=-1)
+    h = _linear(sd, pfx + "cond_x_merge_linear", x_in)
+    st = _linear(sd, pfx + "style_in", style)
+    if sat:
+        h = torch.cat([st.unsqueeze(1), h], dim=1)
+    if tat:
+        h = torch.cat([t1.unsqueeze(1), h], dim=1)
+    ntok = int(tat) + int(sat)
+    kv_len = x_lens + ntok
+    tab = rope_table(T + ntok, bf16_round=True)
+    c = t1.unsqueeze(1)
+    for i in range(L):
+        lp = f"{pfx}transformer.layers.{i}"
+        emb = _linear(sd, lp + ".attention_norm.linear", F.silu(c))
+        sh_a, sc_a, g_a, sh_m, sc_m, g_m = torch.chunk(emb, 6, dim=-1)
+        n = rmsnorm(h, sd[lp + ".attention_norm.norm.weight"]) * (1 + sc_a) + sh_a
+        h = h + g_a * attention(sd, lp + ".attention", n, tab, H, kv_len)
+        n = rmsnorm(h, sd[lp + ".ffn_norm.weight"]) * (1 + sc_m) + sh_m
+        h = h + g_m * feed_forward(sd, lp + ".feed_forward", n)
+    emb = _linear(sd, pfx + "transformer.norm.linear", F.silu(c))
+    scale, shift = torch.chunk(emb, 2, dim=-1)                       # dit_model.py:50-53
+    h = rmsnorm(h, sd[pfx + "transformer.norm.norm.weight"]) * (1 + scale) + shift
+    h = h[:, ntok:]
+    y = _linear(sd, pfx + "final_mlp.2", F.silu(_linear(sd, pfx + "final_mlp.0", h)))
+    return y.transpose(1, 2)
+
+
+def v2_t_span(n_timesteps):
+    """modules/v2/cfm.py:47-48"""
+    t_span = torch.linspace(0, 1, n_timesteps + 1)
+    return t_span + (-1) * (torch.cos(torch.pi / 2 * t_span) - 1 + t_span)
+
+
+def solve_euler_v2(sd, kw, z, x_lens, prompt, mu, style, t_span, cfg_rate=(0.5, 0.5),
+                   random_voice=False, pfx="estimator."):
+    """modules/v2/cfm.py:50-132, per utterance."""
+    B, C, T = z.shape
+    w0, w1 = float(cfg_rate[0]), float(cfg_rate[1])
+    outs = []
+    for b in range(B):
+        Tb = int(x_lens[b])
+        x = z[b:b + 1, :, :Tb].clone()
+        Tp = min(prompt.shape[-1], Tb)
+        px = torch.zeros_like(x)
+        px[..., :Tp] = prompt[b:b + 1, :, :Tp]
+        x[..., :Tp] = 0
+        m, s, xl = mu[b:b + 1, :Tb], style[b:b + 1], torch.tensor([Tb])
+        zp, zs, zm = torch.zeros_like(px), torch.zeros_like(s), torch.zeros_like(m)
+        t = t_span[0]
+        dt = t_span[1] - t_span[0]
+
+        def est(xs, ps, ss, ms):
+            n = len(xs)
+            return dit_v2_forward(sd, kw, torch.cat(xs), torch.cat(ps), xl.repeat(n),
+                                  t.repeat(n), torch.cat(ss), torch.cat(ms), pfx=pfx)
+
+        for step in range(1, len(t_span)):
+            if random_voice:
+                o = est([x, x], [zp, zp], [zs, zs], [m, zm])
+                v = (1.0 + w0) * o[0:1] - w0 * o[1:2]
+            elif w0 == 0 and w1 == 0:
+                v = est([x], [px], [s], [m])
+            elif w0 == 0:
+                o = est([x, x], [px, zp], [s, zs], [m, m])
+                v = (1.0 + w1) * o[0:1] - w1 * o[1:2]
+            elif w1 == 0:
+                o = est([x, x], [px, zp], [s, zs], [m, zm])
+                v = (1.0 + w0) * o[0:1] - w0 * o[1:2]
+            else:
+                o = est([x, x, x], [px, zp, zp], [s, zs, zs], [m, m, zm])
+                v = (1.0 + w0 + w1) * o[0:1] - w0 * o[2:3] - w1 * o[1:2]
+            x = x + dt * v
+            t = t + dt
+            if step < len(t_span) - 1:
+                dt = t_span[step + 1] - t
+            x[:, :, :Tp] = 0
+        outs.append(F.pad(x, (0, T - Tb)))
+    return torch.cat(outs)
+
+
+# ----------------------------------------------------------------------------
+# BigVGAN
+# ----------------------------------------------------------------------------
+def kaiser_sinc_filter12():
+    """modules/bigvgan/alias_free_activation/torch/filter.py:30-62 with
+    cutoff 0.25, half_width 0.3, kernel_size 12 (resample.py:22-24, :47-52)."""
+    ks, cutoff, half_width = 12, 0.25, 0.3
+    half = ks // 2
+    A = 2.285 * (half - 1) * math.pi * 4 * half_width + 7.95
+    beta = 0.1102 * (A - 8.7) if A > 50 else (
+        0.5842 * (A - 21) ** 0.4 + 0.07886 * (A - 21.0) if A >= 21 else 0.0)
+    win = torch.kaiser_window(ks, beta=beta, periodic=False)
+    time = torch.arange(-half, half) + 0.5
+    f = 2 * cutoff * win * torch.sinc(2 * cutoff * time)
+    return f / f.sum()
+
+
+def snake_aa(x, alpha_log, beta_log, h12=None):
+    """Anti-aliased SnakeBeta, closed form of act.py:25-30 + resample.py:29-38 +
+    filter.py:94-101 + activations.py:107-119.  x: (B, C, L)."""
+    if h12 is None:
+        h12 = kaiser_sinc_filter12()
+    B, C, L = x.shape
+    xp = F.pad(x, (5, 5), mode="replicate")
+    u = 2.0 * F.conv_transpose1d(xp, h12.view(1, 1, 12).expand(C, -1, -1), stride=2, groups=C)
+    u = u[..., 15:-15]
+    a = torch.exp(alpha_log).view(1, C, 1)
+    b = torch.exp(beta_log).view(1, C, 1)
+    u = u + (1.0 / (b + 1e-9)) * torch.sin(u * a) ** 2
+    up = F.pad(u, (5, 6), mode="replicate")
+    return F.conv1d(up, h12.view(1, 1, 12).expand(C, -1, -1), stride=2, groups=C)
+
+
+def bigvgan_forward(sd, h, mel):
+    """modules/bigvgan/bigvgan.py:360-386 with AMPBlock1 (:132-141).
+    ``sd`` holds folded weights (after remove_weight_norm) or weight_g/weight_v."""
+    h12 = kaiser_sinc_filter12()
+    nk = len(h.resblock_kernel_sizes)
+    x = F.conv1d(mel, _wn_weight(sd, "conv_pre"), sd["conv_pre.bias"], padding=3)
+    for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+        x = F.conv_transpose1d(x, _wn_weight_convT(sd, f"ups.{i}.0"), sd[f"ups.{i}.0.bias"],
+                               stride=u, padding=(k - u) // 2)
+        xs = None
+        for j in range(nk):
+            rb = f"resblocks.{i * nk + j}"
+            ks = h.resblock_kernel_sizes[j]
+            y = x
+            for l, d in enumerate(h.resblock_dilation_sizes[j]):
+                xt = snake_aa(y, sd[f"{rb}.activations.{2 * l}.act.alpha"],
+                              sd[f"{rb}.activations.{2 * l}.act.beta"], h12)
+                xt = F.conv1d(xt, _wn_weight(sd, f"{rb}.convs1.{l}"), sd[f"{rb}.convs1.{l}.bias"],
+                              dilation=d, padding=d * (ks - 1) // 2)
+                xt = snake_aa(xt, sd[f"{rb}.activations.{2 * l + 1}.act.alpha"],
+                              sd[f"{rb}.activations.{2 * l + 1}.act.beta"], h12)
+                xt = F.conv1d(xt, _wn_weight(sd, f"{rb}.convs2.{l}"), sd[f"{rb}.convs2.{l}.bias"],
+                              padding=(ks - 1) // 2)
+                y = xt + y
+            xs = y if xs is None else xs + y
+        x = xs / nk
+    x = snake_aa(x, sd["activation_post.act.alpha"], sd["activation_post.act.beta"], h12)
+    x = F.conv1d(x, _wn_weight(sd, "conv_post"), sd.get("conv_post.bias"), padding=3)
+    if h.get("use_tanh_at_final", True):
+        return torch.tanh(x)
+    return torch.clamp(x, min=-1.0, max=1.0)
+
+
+def _wn_weight_convT(sd, prefix):
+    """ConvTranspose1d weight (I, O, k): weight_norm dim=0 is per *input* channel
+    (SURVEY section 8 a16)."""
+    return _wn_weight(sd, prefix)

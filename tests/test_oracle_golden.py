@@ -1,0 +1,74 @@
+"""Pin oracle/seedvc_oracle.py to the committed outputs of the real reference
+(tests/golden/*.npz, made by oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import seedvc_b200  # noqa: F401
+from seedvc_b200 import configs, synth
+import seedvc_oracle as orc
+from conftest import load_golden, rel_l2
+
+V1 = ["v1_small_scaled_cfg", "v1_small_scaled_nocfg", "v1_tiny_scaled_cfg", "v1_base_scaled_cfg",
+      "v1_tiny_full", "v1_small_full", "v1_base_full"]
+V2 = ["v2_small_3branch", "v2_small_spk_only", "v2_small_txt_only", "v2_small_nocfg",
+      "v2_small_random_voice"]
+TOL = 2e-5
+
+
+def test_fir_taps_and_snake_kat():
+    g = load_golden("snake_kat")
+    h = orc.kaiser_sinc_filter12()
+    assert np.allclose(h.numpy(), g["filter"], atol=1e-8)
+    # taps quoted in SURVEY App. A.7
+    assert abs(float(h[5]) - 0.4432097971) < 1e-7 and abs(float(h[0]) - 0.0020289647) < 1e-8
+    y0 = orc.snake_aa(torch.tensor(g["x0"]), torch.zeros(4), torch.zeros(4))
+    assert rel_l2(y0, g["y0"]) < 1e-6
+    assert abs(float(y0[0, 0, 0]) - 0.0032857) < 1e-6        # SURVEY section 8c KAT row 0
+    y1 = orc.snake_aa(torch.tensor(g["x1"]), torch.tensor(g["alpha"]), torch.tensor(g["beta"]))
+    assert rel_l2(y1, g["y1"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", V1)
+def test_v1_sampler_matches_reference(name, manifest):
+    g = load_golden(name)
+    m = g["meta"]
+    args = configs.v1_model_params(m["model"])
+    if m["scaled"]:
+        args = configs.scaled_down(args)
+    sd = synth.synth_state_dict(manifest[f"keys_{m['model']}{'_scaled' if m['scaled'] else ''}"])
+    T, Tp = m["T"], m["Tp"]
+    mu, prompt, style, z = synth.synth_batch(1, T, Tp, args.DiT.in_channels, args.DiT.content_dim)
+    t_span = torch.linspace(0, 1, m["n_steps"] + 1)
+    x0 = z.clone()
+    px = torch.zeros_like(x0)
+    px[..., :Tp] = prompt
+    x0[..., :Tp] = 0
+    v0 = orc.dit_v1_forward(sd, args, x0, px, torch.tensor([T]), t_span[0:1], style, mu)
+    assert rel_l2(v0, g["v0"]) < TOL
+    out = orc.solve_euler_v1(sd, args, z, torch.tensor([T]), prompt, mu, style, t_span, m["cfg"])
+    assert rel_l2(out, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", V2)
+def test_v2_sampler_matches_reference(name, manifest):
+    g = load_golden(name)
+    m = g["meta"]
+    kw = configs.v2_estimator_kwargs()
+    sd = synth.synth_state_dict(manifest["keys_v2_small"])
+    mu, prompt, style, z = synth.synth_batch(1, m["T"], m["Tp"], kw["in_channels"], kw["content_dim"])
+    t_span = orc.v2_t_span(m["n_steps"])
+    out = orc.solve_euler_v2(sd, kw, z, torch.tensor([m["T"]]), prompt, mu, style, t_span,
+                             m["cfg"], m["random_voice"])
+    assert rel_l2(out, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["bigvgan_22k_t12", "bigvgan_22k_b2_t7"])
+def test_bigvgan_matches_reference(name, manifest):
+    g = load_golden(name)
+    m = g["meta"]
+    h = configs.bigvgan_h(m["config"])
+    sd = synth.synth_state_dict(manifest["keys_" + m["config"]])
+    mel = synth.synth_mel(m["B"], h.num_mels, m["Tm"])
+    wav = orc.bigvgan_forward(sd, h, mel)
+    assert rel_l2(wav, g["wav"]) < TOL
