@@ -1,0 +1,182 @@
+/* seedvc_b200 - C ABI of the B200 (sm_100a) kernels behind Seed-VC's conversion hot path.
+ *
+ * The reference has no FFI on this path except one JIT-built pybind op
+ * (modules/bigvgan/alias_free_activation/cuda/anti_alias_activation.cpp:19-22,
+ * `fwd_cuda` in anti_alias_activation_cuda.cu:212-246): raw device pointers in,
+ * launch on the caller's stream, dtype dispatch, no allocation of inputs.  This
+ * header keeps that shape for every kernel of the path: plain pointers, sizes and
+ * a cudaStream_t (passed as void*), no torch types, no allocation, no host sync.
+ * Each entry point names the reference site it replaces.  See INTEGRATION.md for
+ * the ctypes binding.
+ *
+ * Return value: SVC_OK, or a negative SVC_ERR_* code with a message available
+ * from svc_last_error().  All launches are asynchronous on `stream`.
+ *
+ * Layout convention: activations are "frames-major" (B, T, C): channel/feature
+ * index contiguous.  A `rows`/`bstride`/`rstride` triple describes a strided
+ * (B, rows, C) view in ELEMENTS of the tensor's own dtype.
+ */
+#ifndef SEEDVC_B200_H_
+#define SEEDVC_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVC_OK 0
+#define SVC_ERR_ARG (-1)
+#define SVC_ERR_CUDA (-2)
+#define SVC_ERR_UNSUPPORTED (-3)
+
+/* operand element types */
+#define SVC_BF16 0 /* bf16 operands, tcgen05 tensor cores, fp32 accumulate */
+#define SVC_F32 1  /* fp32 operands, fp32 FFMA ("fp32 mode", also small-M GEMMs) */
+
+/* svc_gemm backends */
+#define SVC_BACKEND_AUTO 0 /* bf16 -> tcgen05, fp32 -> SIMT */
+#define SVC_BACKEND_SIMT 1 /* force the SIMT mainloop (debug cross-check) */
+
+/* epilogue activations */
+#define SVC_ACT_NONE 0
+#define SVC_ACT_SILU 1
+#define SVC_ACT_SWIGLU_PAIR 2  /* out[j] = silu(v[2j]) * v[2j+1]            (FeedForward) */
+#define SVC_ACT_TANH_SIG_PAIR 3 /* out[j] = tanh(v[2j]) * sigmoid(v[2j+1])  (WaveNet gate) */
+#define SVC_ACT_ROPE 4          /* rotate pairs (2j,2j+1) of columns < rope_cols       */
+
+#define SVC_MAX_SEG 16
+
+const char* svc_last_error(void);
+int svc_version(void);
+
+/* ---------------------------------------------------------------------------
+ * svc_gemm: out[b,t,:] = epilogue( sum_s A_s[b, t + shift_s, 0:K_s] . W_s[:, 0:K_s]^T )
+ *
+ * One call covers every dense contraction of the path:
+ *   nn.Linear          (diffusion_transformer.py:205-206,266-268,166,437,476-478,...)  1 segment
+ *   concat + Linear    (diffusion_transformer.py:185-186, 524-525)  2 segments, no cat
+ *   Conv1d, k taps     (bigvgan.py:56-87,285-287,348-350; wavenet.py:125-135)  k segments
+ *   ConvTranspose1d    (bigvgan.py:300-316)  3 segments over the polyphase weight
+ * Rows of A outside [0, a_rows) read as zero (conv zero padding / TMA OOB fill).
+ * W_s is (N, K_s) row-major with row stride w_rstride.
+ * Epilogue order: v = acc + bias[n] + rowbias[b][n]; act (pair acts halve N);
+ *   v *= gate[b][n]; v += res[b,t,n]; v *= alpha; if (accumulate) v += out_f32[b,t,n];
+ *   store out_f32 and/or out_op (operand dtype).
+ * ------------------------------------------------------------------------- */
+typedef struct svc_gemm_desc {
+    int dtype;  /* SVC_BF16 / SVC_F32: element type of A, W and out_op */
+    int B, T, N; /* output rows per batch, GEMM columns (before pair reduction) */
+    int n_seg;
+    const void* a_ptr[SVC_MAX_SEG];
+    long long a_bstride[SVC_MAX_SEG];
+    long long a_rstride[SVC_MAX_SEG];
+    int a_rows[SVC_MAX_SEG];  /* valid rows per batch of the A view */
+    int a_shift[SVC_MAX_SEG]; /* row offset added to t */
+    const void* w_ptr[SVC_MAX_SEG];
+    long long w_rstride[SVC_MAX_SEG];
+    int K[SVC_MAX_SEG];
+    /* epilogue */
+    const float* bias;    /* [N] or NULL */
+    const float* rowbias; /* [B][N] (stride rowbias_bstride) or NULL */
+    long long rowbias_bstride;
+    int act;
+    const float* rope_tab; /* (pos, 32, 2) cos/sin, used when act == SVC_ACT_ROPE */
+    int rope_cols;         /* columns [0, rope_cols) are rotated (q and k) */
+    int rope_pos0;         /* position of row t is rope_pos0 + t */
+    int q_cols;            /* columns [0, q_cols) are multiplied by q_scale after RoPE */
+    float q_scale;
+    const float* gate; /* [B][N_out] (stride gate_bstride) or NULL */
+    long long gate_bstride;
+    const float* res; /* fp32 (B, T, N_out) view or NULL */
+    long long res_bstride, res_rstride;
+    float alpha;
+    int accumulate;
+    float* out_f32; /* or NULL */
+    long long of_bstride, of_rstride;
+    void* out_op; /* operand dtype, or NULL */
+    long long oo_bstride, oo_rstride;
+} svc_gemm_desc;
+
+int svc_gemm(const svc_gemm_desc* d, int backend, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * svc_attention: non-causal softmax attention with key-length masking.
+ * Replaces F.scaled_dot_product_attention + the (B,1,T,T) bool mask
+ * (diffusion_transformer.py:255, 518-520).  q/k/v are (B, T, H*64) views with a
+ * common bstride/rstride (column slices of the packed wqkv output); RoPE and the
+ * 1/sqrt(64) scale are already applied to q,k by the wqkv epilogue.
+ * kv_len[b] keys are attended for batch b (device int32 [B]).  head_dim is 64.
+ * ------------------------------------------------------------------------- */
+int svc_attention(const void* q, const void* k, const void* v, long long qkv_bstride,
+                  long long qkv_rstride, void* out, long long out_bstride, long long out_rstride,
+                  int B, int T, int H, const int* kv_len, int dtype, int backend, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * svc_norm_mod: out = norm(x) * gamma * mul + add, per row.
+ *   mode 0: RMSNorm (diffusion_transformer.py:274-285) as used by AdaptiveLayerNorm
+ *           (:30-48; v2 dit_model.py:20-54,136-142); gamma = norm.weight.
+ *   mode 1: LayerNorm without affine, eps 1e-6 (FinalLayer, :391,401-403).
+ * gamma/mul/add are [D] fp32 vectors or NULL.  x is fp32 (B, T, D) strided; out is the
+ * operand dtype.
+ * ------------------------------------------------------------------------- */
+int svc_norm_mod(const float* x, long long x_bstride, long long x_rstride, const float* gamma,
+                 const float* mul, const float* add, float eps, int mode, void* out,
+                 long long o_bstride, long long o_rstride, int B, int T, int D, int out_dtype,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------
+ * svc_snake_aa: anti-aliased Snake / SnakeBeta = 2x Kaiser-sinc FIR upsample, x + sin^2(a x)/b,
+ * FIR low-pass + 2x downsample.  Replaces Activation1d (alias_free_activation/torch/act.py:25-30,
+ * resample.py:29-38, filter.py:94-101, activations.py:107-119) and the reference's own CUDA op
+ * (alias_free_activation/cuda/anti_alias_activation_cuda.cu:44-179).
+ * x: contiguous (B, L, C), fp32 or bf16 (x_dtype); out: contiguous (B, L, C) out_dtype.
+ * a[c] = exp(alpha_c) (or alpha_c), inv_b[c] = 1 / (beta_c + 1e-9), prepared by the caller.
+ * ------------------------------------------------------------------------- */
+int svc_snake_aa(const void* x, int x_dtype, void* out, int out_dtype, const float* a,
+                 const float* inv_b, int B, int L, int C, int precise, void* stream);
+
+/* activation_post + conv_post + clamp/tanh (bigvgan.py:377-384): out (B, L) fp32.
+ * w is (ksize, C) fp32 (tap-major), bias NULL when use_bias_at_final is false. */
+int svc_snake_conv_post(const float* x, const float* a, const float* inv_b, const float* w,
+                        const float* bias, float* out, int B, int L, int C, int ksize,
+                        int use_tanh, int precise, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * svc_cfg_euler: x += dt * (c0 v[0] + c1 v[1] + c2 v[2]); rows t < prompt_len and rows
+ * t >= x_lens[b] are set to 0; optionally also writes x in the operand dtype.
+ * Replaces flow_matching.py:98-110 and v2/cfm.py:86-130.  x: (B, T, C) fp32 contiguous;
+ * v: (n_branch*B, T, C) fp32 contiguous, branch-major.
+ * ------------------------------------------------------------------------- */
+int svc_cfg_euler(float* x, const float* v, int n_branch, float c0, float c1, float c2, float dt,
+                  int B, int T, int C, int prompt_len, const int* x_lens, void* x_op, int op_dtype,
+                  void* stream);
+
+/* (B, C, T) fp32 -> (B, T, C) in out_dtype; rows t in [zero_from, zero_to) are written as 0.
+ * Entry of the sampler/vocoder (flow_matching.py:76-81; diffusion_transformer.py:503-504). */
+int svc_bct_to_btc(const float* in, void* out, long long o_bstride, long long o_rstride, int B,
+                   int C, int T, int zero_from, int zero_to, int out_dtype, void* stream);
+/* (B, T, C) fp32 -> (B, C, T) fp32 */
+int svc_btc_to_bct(const float* in, float* out, int B, int T, int C, void* stream);
+
+/* fp32 -> operand dtype, n contiguous elements */
+int svc_cast(const float* in, void* out, long long n, int out_dtype, void* stream);
+
+/* Reflect padding halo of the WaveNet input (encodec.py:212-228 `pad1d(..., 'reflect')`):
+ * buf is (B, T + 2*pad, C) in the operand dtype with the body at rows [pad, pad+len_b);
+ * writes rows pad-1-i <- body[i+1] and pad+len_b+i <- body[len_b-2-i], i in [0,pad). */
+int svc_reflect_halo(void* buf, long long bstride, long long rstride, int B, int T, int C, int pad,
+                     const int* lens, int dtype, void* stream);
+
+/* Sinusoidal timestep features (diffusion_transformer.py:341-359): out (n, 2*half) =
+ * [cos(1000 t f_i) | sin(1000 t f_i)], f_i = freqs[i] = exp(-ln(1e4) i / half) (the module's
+ * `freqs` buffer, :337-340). */
+int svc_timestep_embedding(const float* t, const float* freqs, float* out, int n, int half,
+                           void* stream);
+
+/* dst[b, 0:D] = src[b * src_bstride + 0:D] for b < B (token rows, diffusion_transformer.py:512-517) */
+int svc_set_rows(const float* src, long long src_bstride, float* dst, long long dst_bstride, int B,
+                 int D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEEDVC_B200_H_ */

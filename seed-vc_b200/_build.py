@@ -1,0 +1,71 @@
+"""Ahead-of-time build of ``libseedvc_b200.so`` (nvcc, sm_100a only).
+
+The reference JIT-builds its one CUDA op at import time for sm_70/sm_80
+(modules/bigvgan/alias_free_activation/cuda/load.py:17-65); here the library is
+built in-tree, explicitly, for ``compute_100a`` so it travels with the repo.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libseedvc_b200.so")
+SOURCES = ["gemm.cu", "attention.cu", "elementwise.cu", "snake.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
+    "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+]
+
+
+def _nvcc() -> str:
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    return "nvcc"
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(ROOT, "include", "seedvc_b200.h"))
+    objs, jobs = [], []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _stale(obj, [src] + headers):
+            jobs.append([_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj])
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+        return r.stderr
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        logs = list(ex.map(run, jobs))
+    if jobs or force or _stale(LIB, objs):
+        run([_nvcc(), "-shared", "-o", LIB] + objs +
+            ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
+    if jobs:
+        with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
+            f.write("\n".join(logs))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,246 @@
+"""BigVGAN-v2 generator on the sm_100a kernels, API-compatible with the reference.
+
+Drop-in surface: ``BigVGAN(h, use_cuda_kernel=False)``, ``from_pretrained``, ``remove_weight_norm``,
+``forward(mel (B, n_mels, Tm)) -> (B, 1, Tm * hop)`` (reference: modules/bigvgan/bigvgan.py:266-491).
+
+Execution plan per call (frames-major activations, fp32 residual stream, operand-dtype GEMM inputs):
+  conv_pre                      7-tap segmented GEMM                           bigvgan.py:285-287,362
+  per stage i:
+    ups[i] ConvTranspose1d      polyphase: 3-tap GEMM with N = stride * C_out   :300-316,367
+    3 x AMPBlock1               6 x (svc_snake_aa -> k-tap dilated GEMM), residual and the
+                                (r0 + r1 + r2) / 3 average fused in GEMM epilogues   :132-141,369-375
+  activation_post + conv_post + clamp   one fused kernel                        :377-384
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import torch
+from torch import nn
+
+from . import synth
+from .configs import AttrDict, to_attr
+from .flow_matching import _Params
+from .ops import Ops
+
+
+class _Act(nn.Module):
+    """Activation1d(SnakeBeta): parameters + the two FIR buffers of the reference."""
+
+    def __init__(self, ch, filt):
+        super().__init__()
+        self.act = _Params(alpha=(ch,), beta=(ch,))
+        self.upsample = nn.Module()
+        self.upsample.register_buffer("filter", filt.clone())
+        self.downsample = nn.Module()
+        self.downsample.lowpass = nn.Module()
+        self.downsample.lowpass.register_buffer("filter", filt.clone())
+
+
+class _AMPBlock(nn.Module):
+    def __init__(self, ch, k, n_dil, filt):
+        super().__init__()
+        self.convs1 = nn.ModuleList([_Params(weight=(ch, ch, k), bias=(ch,)) for _ in range(n_dil)])
+        self.convs2 = nn.ModuleList([_Params(weight=(ch, ch, k), bias=(ch,)) for _ in range(n_dil)])
+        self.activations = nn.ModuleList([_Act(ch, filt) for _ in range(2 * n_dil)])
+
+
+def kaiser_sinc_filter12():
+    """Same taps as the kernel's constant table (filter.py:30-62 with 0.25 / 0.3 / 12)."""
+    import math
+    ks, cutoff, half_width = 12, 0.25, 0.3
+    half = ks // 2
+    A = 2.285 * (half - 1) * math.pi * 4 * half_width + 7.95
+    beta = 0.1102 * (A - 8.7)
+    win = torch.kaiser_window(ks, beta=beta, periodic=False)
+    time = torch.arange(-half, half) + 0.5
+    f = 2 * cutoff * win * torch.sinc(2 * cutoff * time)
+    return (f / f.sum()).view(1, 1, ks)
+
+
+class BigVGAN(nn.Module):
+    def __init__(self, h, use_cuda_kernel: bool = False, mode: str = "bf16"):
+        super().__init__()
+        self.h = h if isinstance(h, AttrDict) else to_attr(dict(h))
+        self.h["use_cuda_kernel"] = use_cuda_kernel      # accepted; the sm_100a kernels always run
+        h = self.h
+        if h.resblock != "1":
+            raise NotImplementedError("only AMPBlock1 (resblock '1'); AMPBlock2.forward returns None "
+                                      "in the reference (SURVEY App. D-7)")
+        if h.activation not in ("snake", "snakebeta"):
+            raise NotImplementedError("activation incorrectly specified")
+        self.num_kernels = len(h.resblock_kernel_sizes)
+        self.num_upsamples = len(h.upsample_rates)
+        filt = kaiser_sinc_filter12()
+        c0 = h.upsample_initial_channel
+        self.conv_pre = _Params(weight=(c0, h.num_mels, 7), bias=(c0,))
+        self.ups = nn.ModuleList()
+        self.resblocks = nn.ModuleList()
+        ch = c0
+        for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+            self.ups.append(nn.ModuleList([_Params(weight=(c0 // 2 ** i, c0 // 2 ** (i + 1), k),
+                                                   bias=(c0 // 2 ** (i + 1),))]))
+            ch = c0 // 2 ** (i + 1)
+            for ks, dil in zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes):
+                self.resblocks.append(_AMPBlock(ch, ks, len(dil), filt))
+        self.activation_post = _Act(ch, filt)
+        self.use_bias_at_final = h.get("use_bias_at_final", True)
+        self.conv_post = _Params(weight=(1, ch, 7), **({"bias": (1,)} if self.use_bias_at_final else {}))
+        self.use_tanh_at_final = h.get("use_tanh_at_final", True)
+        synth.fill_parameters_(self, seed=0)
+        self.mode = mode
+        self._w = None
+        self._w_key = None
+        self._register_load_state_dict_pre_hook(self._fold_weight_norm_hook)
+
+    # -- reference API ---------------------------------------------------------------------
+    def remove_weight_norm(self):
+        """Weights are always held folded; checkpoints with weight_g / weight_v are folded on load."""
+        return None
+
+    @staticmethod
+    def _fold_weight_norm_hook(state_dict, prefix, *args):
+        for k in [k for k in state_dict if k.endswith("weight_g")]:
+            base = k[: -len("weight_g")]
+            g, v = state_dict.pop(k), state_dict.pop(base + "weight_v")
+            n = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+            state_dict[base + "weight"] = g * v / n        # norm over all dims but 0 (App. a16)
+
+    @classmethod
+    def from_pretrained(cls, model_id, use_cuda_kernel=False, mode="bf16", **ignored):
+        """Local-directory loader (config.json + bigvgan_generator.pt with key 'generator'),
+        the layout the reference's save_pretrained writes (bigvgan.py:403-411).  Hub download is
+        out of scope (no network); extra HF kwargs are accepted and ignored (App. D-9)."""
+        if not os.path.isdir(model_id):
+            raise FileNotFoundError(f"{model_id}: from_pretrained needs a local directory")
+        with open(os.path.join(model_id, "config.json")) as f:
+            h = to_attr(json.load(f))
+        model = cls(h, use_cuda_kernel=use_cuda_kernel, mode=mode)
+        ck = torch.load(os.path.join(model_id, "bigvgan_generator.pt"), map_location="cpu")
+        model.load_state_dict(ck["generator"])
+        return model
+
+    def set_mode(self, mode):
+        if mode != self.mode:
+            self.mode, self._w = mode, None
+
+    # -- kernel-side weights ----------------------------------------------------------------
+    def _prepare(self):
+        dev = self.conv_pre.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("seedvc_b200.BigVGAN runs on CUDA only: call .to('cuda') first "
+                               "(there is no CPU fallback)")
+        key = (str(dev), self.mode, tuple(p._version for p in self.parameters()),
+               tuple(p.data_ptr() for p in self.parameters()))
+        if self._w is None or key != self._w_key:
+            self._w, self._w_key = self._build_weights(Ops(self.mode)), key
+        return self._w
+
+    def _build_weights(self, ops):
+        """Fold / permute / cast the parameters into what the kernels read."""
+        od = ops.op_dtype
+        h = self.h
+        logscale = bool(h.get("snake_logscale", False))
+        is_beta = h.activation == "snakebeta"
+
+        def conv_w(p):                       # (O, I, k) -> (k, O, I) operand dtype
+            return p.weight.detach().float().permute(2, 0, 1).contiguous().to(od)
+
+        def f32(t):
+            return t.detach().float().contiguous()
+
+        def snake(a):
+            alpha = a.act.alpha.detach().float()
+            beta = a.act.beta.detach().float() if is_beta else alpha
+            if logscale:
+                alpha, beta = torch.exp(alpha), torch.exp(beta)
+            return alpha.contiguous(), (1.0 / (beta + 1e-9)).contiguous()
+
+        w = {"ops": ops, "pre_w": conv_w(self.conv_pre), "pre_b": f32(self.conv_pre.bias)}
+        stages = []
+        for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+            wt = self.ups[i][0].weight.detach().float()          # (I, O, k)
+            I, O, _ = wt.shape
+            pad = (k - u) // 2
+            # polyphase: out[u*q + r] = sum_delta x[q + delta] . w[:, :, r + pad - u*delta]
+            dmin = min(-((-(r + pad - k + 1)) // u) for r in range(u))   # ceil((r+pad-k+1)/u)
+            dmax = max((r + pad) // u for r in range(u))
+            deltas = list(range(dmin, dmax + 1))
+            poly = torch.zeros(len(deltas), u * O, I, device=wt.device)
+            for di, dl in enumerate(deltas):
+                for r in range(u):
+                    kk = r + pad - u * dl
+                    if 0 <= kk < k:
+                        poly[di, r * O:(r + 1) * O, :] = wt[:, :, kk].t()
+            st = {"u": u, "O": O, "deltas": deltas, "up_w": poly.to(od).contiguous(),
+                  "up_b": f32(self.ups[i][0].bias).repeat(u).contiguous(), "blocks": []}
+            for j in range(self.num_kernels):
+                rb = self.resblocks[i * self.num_kernels + j]
+                ks = h.resblock_kernel_sizes[j]
+                pairs = []
+                for l, d in enumerate(h.resblock_dilation_sizes[j]):
+                    pairs.append({
+                        "d": d, "k": ks,
+                        "a1": snake(rb.activations[2 * l]), "a2": snake(rb.activations[2 * l + 1]),
+                        "w1": conv_w(rb.convs1[l]), "b1": f32(rb.convs1[l].bias),
+                        "w2": conv_w(rb.convs2[l]), "b2": f32(rb.convs2[l].bias),
+                    })
+                st["blocks"].append(pairs)
+            stages.append(st)
+        w["stages"] = stages
+        w["post_a"] = snake(self.activation_post)
+        w["post_w"] = f32(self.conv_post.weight[0].t())           # (k, C)
+        w["post_b"] = f32(self.conv_post.bias) if self.use_bias_at_final else None
+        return w
+
+    @torch.no_grad()
+    def forward(self, x):
+        w = self._prepare()
+        ops: Ops = w["ops"]
+        od = ops.op_dtype
+        dev = x.device
+        B, n_mels, Tm = x.shape
+        f32 = torch.float32
+        mel_op = ops.empty(B, Tm, n_mels, device=dev)
+        ops.bct_to_btc(x.float().contiguous(), mel_op)
+        c0 = self.h.upsample_initial_channel
+        cur_op = ops.empty(B, Tm, c0, device=dev)
+        ops.gemm([(mel_op, j - 3, w["pre_w"][j]) for j in range(7)], c0, B=B, T=Tm, bias=w["pre_b"],
+                 out_op=cur_op)
+        L = Tm
+        cur = None
+        nk = self.num_kernels
+        for si, st in enumerate(w["stages"]):
+            u, O = st["u"], st["O"]
+            xs = torch.empty(B, L * u, O, dtype=f32, device=dev)
+            ops.gemm([(cur_op, dl, st["up_w"][di]) for di, dl in enumerate(st["deltas"])], u * O,
+                     B=B, T=L, bias=st["up_b"], out_f32=xs.view(B, L, u * O))
+            L = L * u
+            act = torch.empty(B, L, O, dtype=od, device=dev)
+            xt = torch.empty(B, L, O, dtype=f32, device=dev)
+            y = torch.empty(B, L, O, dtype=f32, device=dev)
+            nxt = torch.empty(B, L, O, dtype=f32, device=dev)
+            last_stage = si == len(w["stages"]) - 1
+            nxt_op = None if last_stage else torch.empty(B, L, O, dtype=od, device=dev)
+            for j, pairs in enumerate(st["blocks"]):
+                src = xs
+                for l, pr in enumerate(pairs):
+                    k, d = pr["k"], pr["d"]
+                    half = (k - 1) // 2
+                    ops.snake(src, act, *pr["a1"])
+                    ops.gemm([(act, (t - half) * d, pr["w1"][t]) for t in range(k)], O, B=B, T=L,
+                             bias=pr["b1"], out_f32=xt)
+                    ops.snake(xt, act, *pr["a2"])
+                    segs = [(act, t - half, pr["w2"][t]) for t in range(k)]
+                    if l < len(pairs) - 1:
+                        ops.gemm(segs, O, B=B, T=L, bias=pr["b2"], res=src, out_f32=y)
+                        src = y
+                    else:   # last pair: residual, then (r0 + r1 + r2) / 3 accumulated in place
+                        ops.gemm(segs, O, B=B, T=L, bias=pr["b2"], res=src, alpha=1.0 / nk,
+                                 accumulate=j > 0, out_f32=nxt,
+                                 out_op=nxt_op if j == nk - 1 else None)
+            cur, cur_op = nxt, nxt_op
+        out = torch.empty(B, L, dtype=f32, device=dev)
+        ops.snake_conv_post(cur, *w["post_a"], w["post_w"], w["post_b"], out, self.use_tanh_at_final)
+        return out.view(B, 1, L)

@@ -1,0 +1,372 @@
+// Memory-bound kernels of the sampler: AdaLN / RMSNorm / LayerNorm modulation, CFG combine +
+// Euler update, layout changes at the API boundary, reflect halo, timestep features.
+// All are vectorised, coalesced HBM streaming kernels; reductions use warp shuffles.
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace svc {
+
+// ------------------------------------------------------------------------------------------
+// svc_norm_mod: one warp per row.  Reference: AdaptiveLayerNorm / RMSNorm / FinalLayer norm
+// (modules/diffusion_transformer.py:30-48,274-285,401-403; v2 modules/v2/dit_model.py:20-54).
+// ------------------------------------------------------------------------------------------
+template <typename TO, int MAXV>
+__global__ void __launch_bounds__(256) norm_mod_kernel(
+    const float* __restrict__ x, long long x_bstride, long long x_rstride,
+    const float* __restrict__ gamma, const float* __restrict__ mul, const float* __restrict__ add,
+    float eps, int mode, TO* __restrict__ out, long long o_bstride, long long o_rstride, int B, int T,
+    int D) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B * T) return;
+    const int b = warp / T, t = warp % T;
+    const float* xr = x + static_cast<long long>(b) * x_bstride + static_cast<long long>(t) * x_rstride;
+    float4 v[MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < D) {
+            v[i] = __ldg(reinterpret_cast<const float4*>(xr + c));
+            s1 += v[i].x + v[i].y + v[i].z + v[i].w;
+            s2 += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+        }
+    }
+    float mean = 0.f, rstd;
+    if (mode == 0) {
+        s2 = warp_sum(s2);
+        rstd = rsqrtf(s2 / D + eps);
+    } else {
+        s1 = warp_sum(s1);
+        mean = s1 / D;
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            if (c < D) {
+                const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean,
+                            a3 = v[i].w - mean;
+                var += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+            }
+        }
+        var = warp_sum(var);
+        rstd = rsqrtf(var / D + eps);
+    }
+    TO* orow = out + static_cast<long long>(b) * o_bstride + static_cast<long long>(t) * o_rstride;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (c < D) {
+            float y[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd,
+                          (v[i].w - mean) * rstd};
+            if (gamma != nullptr) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+                y[0] *= g.x, y[1] *= g.y, y[2] *= g.z, y[3] *= g.w;
+            }
+            if (mul != nullptr) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(mul + c));
+                y[0] *= g.x, y[1] *= g.y, y[2] *= g.z, y[3] *= g.w;
+            }
+            if (add != nullptr) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(add + c));
+                y[0] += g.x, y[1] += g.y, y[2] += g.z, y[3] += g.w;
+            }
+            if constexpr (sizeof(TO) == 4) {
+                *reinterpret_cast<float4*>(orow + c) = make_float4(y[0], y[1], y[2], y[3]);
+            } else {
+                uint2 q;
+                q.x = pack_bf16(y[0], y[1]);
+                q.y = pack_bf16(y[2], y[3]);
+                *reinterpret_cast<uint2*>(orow + c) = q;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// svc_cfg_euler.  Reference: modules/flow_matching.py:98-110, modules/v2/cfm.py:86-130.
+// ------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void __launch_bounds__(256) cfg_euler_kernel(
+    float* __restrict__ x, const float* __restrict__ v, int n_branch, float c0, float c1, float c2,
+    float dt, int B, int T, int C, int prompt_len, const int* __restrict__ x_lens,
+    TO* __restrict__ x_op, bool write_op) {
+    const long long n4 = static_cast<long long>(B) * T * C / 4;
+    const long long per_branch = static_cast<long long>(B) * T * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long e = i * 4;
+        const int t = static_cast<int>((e / C) % T);
+        const int b = static_cast<int>(e / (static_cast<long long>(C) * T));
+        float4 xv = *reinterpret_cast<const float4*>(x + e);
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(v + e));
+        float4 d = make_float4(c0 * v0.x, c0 * v0.y, c0 * v0.z, c0 * v0.w);
+        if (n_branch > 1) {
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(v + per_branch + e));
+            d.x = fmaf(c1, v1.x, d.x), d.y = fmaf(c1, v1.y, d.y), d.z = fmaf(c1, v1.z, d.z),
+            d.w = fmaf(c1, v1.w, d.w);
+        }
+        if (n_branch > 2) {
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(v + 2 * per_branch + e));
+            d.x = fmaf(c2, v2.x, d.x), d.y = fmaf(c2, v2.y, d.y), d.z = fmaf(c2, v2.z, d.z),
+            d.w = fmaf(c2, v2.w, d.w);
+        }
+        xv.x = fmaf(dt, d.x, xv.x), xv.y = fmaf(dt, d.y, xv.y), xv.z = fmaf(dt, d.z, xv.z),
+        xv.w = fmaf(dt, d.w, xv.w);
+        const bool dead = t < prompt_len || (x_lens != nullptr && t >= x_lens[b]);
+        if (dead) xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(x + e) = xv;
+        if (write_op) {
+            if constexpr (sizeof(TO) == 4) {
+                *reinterpret_cast<float4*>(x_op + e) = xv;
+            } else {
+                uint2 q;
+                q.x = pack_bf16(xv.x, xv.y);
+                q.y = pack_bf16(xv.z, xv.w);
+                *reinterpret_cast<uint2*>(x_op + e) = q;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// layout changes
+// ------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void __launch_bounds__(256) bct_to_btc_kernel(const float* __restrict__ in, TO* __restrict__ out,
+                                                         long long o_bstride, long long o_rstride,
+                                                         int C, int T, int zero_from, int zero_to) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, t = t0 + tx;
+        tile[i][tx] = (c < C && t < T) ? in[(static_cast<long long>(b) * C + c) * T + t] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int t = t0 + i, c = c0 + tx;
+        if (t < T && c < C) {
+            float v = tile[tx][i];
+            if (t >= zero_from && t < zero_to) v = 0.f;
+            out[static_cast<long long>(b) * o_bstride + static_cast<long long>(t) * o_rstride + c] =
+                from_f32<TO>(v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) btc_to_bct_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                         int T, int C) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int t = t0 + i, c = c0 + tx;
+        tile[i][tx] = (t < T && c < C) ? in[(static_cast<long long>(b) * T + t) * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, t = t0 + tx;
+        if (c < C && t < T) out[(static_cast<long long>(b) * C + c) * T + t] = tile[tx][i];
+    }
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, TO* __restrict__ out,
+                                                   long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        out[i] = from_f32<TO>(in[i]);
+}
+
+// Reflect halo.  Reference: modules/encodec.py:96-113,212-228 (pad1d 'reflect' in SConv1d).
+template <typename TO>
+__global__ void reflect_halo_kernel(TO* __restrict__ buf, long long bstride, long long rstride, int T,
+                                    int C, int pad, const int* __restrict__ lens) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x;  // 0..2*pad-1
+    int len = lens != nullptr ? lens[b] : T;
+    len = max(2, min(len, T));
+    TO* base = buf + static_cast<long long>(b) * bstride;
+    int dst, src;
+    if (i < pad) {
+        dst = pad - 1 - i;          // left halo row
+        src = pad + (i + 1);        // body row i+1
+    } else {
+        const int k = i - pad;
+        dst = pad + len + k;        // right halo row
+        src = pad + (len - 2 - k);  // body row len-2-k
+    }
+    src = max(src, 0);
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        base[static_cast<long long>(dst) * rstride + c] = base[static_cast<long long>(src) * rstride + c];
+}
+
+// Reference: modules/diffusion_transformer.py:341-359.
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ freqs,
+                                          float* __restrict__ out, int n, int half) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    for (int j = threadIdx.x; j < half; j += blockDim.x) {
+        const float a = 1000.0f * t[i] * freqs[j];
+        out[i * 2 * half + j] = cosf(a);
+        out[i * 2 * half + half + j] = sinf(a);
+    }
+}
+
+__global__ void set_rows_kernel(const float* __restrict__ src, long long src_bstride,
+                                float* __restrict__ dst, long long dst_bstride, int D) {
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < D; c += blockDim.x)
+        dst[static_cast<long long>(b) * dst_bstride + c] = src[static_cast<long long>(b) * src_bstride + c];
+}
+
+static inline bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+}  // namespace svc
+
+using namespace svc;
+
+extern "C" int svc_norm_mod(const float* x, long long x_bstride, long long x_rstride,
+                            const float* gamma, const float* mul, const float* add, float eps,
+                            int mode, void* out, long long o_bstride, long long o_rstride, int B,
+                            int T, int D, int out_dtype, void* stream) {
+    if (D % 4 != 0 || D > 2048 || B < 1 || T < 1) {
+        svc_set_error("svc_norm_mod: D must be a multiple of 4 and <= 2048");
+        return SVC_ERR_ARG;
+    }
+    const int esz = out_dtype == SVC_F32 ? 4 : 2;
+    if (!aligned16(x) || (x_bstride % 4) || (x_rstride % 4) || !aligned16(out) ||
+        (o_bstride * esz) % 8 || (o_rstride * esz) % 8 || (gamma && !aligned16(gamma)) ||
+        (mul && !aligned16(mul)) || (add && !aligned16(add))) {
+        svc_set_error("svc_norm_mod: misaligned pointer or stride");
+        return SVC_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long rows = static_cast<long long>(B) * T;
+    const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+#define LAUNCH_NORM(TO, MAXV)                                                                   \
+    norm_mod_kernel<TO, MAXV><<<blocks, 256, 0, st>>>(x, x_bstride, x_rstride, gamma, mul, add, \
+                                                      eps, mode, static_cast<TO*>(out),         \
+                                                      o_bstride, o_rstride, B, T, D)
+    if (out_dtype == SVC_F32) {
+        if (D <= 512) LAUNCH_NORM(float, 4);
+        else if (D <= 1024) LAUNCH_NORM(float, 8);
+        else LAUNCH_NORM(float, 16);
+    } else {
+        if (D <= 512) LAUNCH_NORM(__nv_bfloat16, 4);
+        else if (D <= 1024) LAUNCH_NORM(__nv_bfloat16, 8);
+        else LAUNCH_NORM(__nv_bfloat16, 16);
+    }
+#undef LAUNCH_NORM
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_cfg_euler(float* x, const float* v, int n_branch, float c0, float c1, float c2,
+                             float dt, int B, int T, int C, int prompt_len, const int* x_lens,
+                             void* x_op, int op_dtype, void* stream) {
+    if (C % 4 != 0 || n_branch < 1 || n_branch > 3 || !aligned16(x) || !aligned16(v) ||
+        (x_op && !aligned16(x_op))) {
+        svc_set_error("svc_cfg_euler: C must be a multiple of 4, 1..3 branches, aligned pointers");
+        return SVC_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n4 = static_cast<long long>(B) * T * C / 4;
+    const unsigned blocks = static_cast<unsigned>(std::min<long long>((n4 + 255) / 256, kNumSMs * 16));
+    if (op_dtype == SVC_F32)
+        cfg_euler_kernel<float><<<blocks, 256, 0, st>>>(x, v, n_branch, c0, c1, c2, dt, B, T, C,
+                                                        prompt_len, x_lens, static_cast<float*>(x_op),
+                                                        x_op != nullptr);
+    else
+        cfg_euler_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+            x, v, n_branch, c0, c1, c2, dt, B, T, C, prompt_len, x_lens,
+            static_cast<__nv_bfloat16*>(x_op), x_op != nullptr);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_bct_to_btc(const float* in, void* out, long long o_bstride, long long o_rstride,
+                              int B, int C, int T, int zero_from, int zero_to, int out_dtype,
+                              void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+    if (out_dtype == SVC_F32)
+        bct_to_btc_kernel<float><<<grid, 256, 0, st>>>(in, static_cast<float*>(out), o_bstride,
+                                                       o_rstride, C, T, zero_from, zero_to);
+    else
+        bct_to_btc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+            in, static_cast<__nv_bfloat16*>(out), o_bstride, o_rstride, C, T, zero_from, zero_to);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_btc_to_bct(const float* in, float* out, int B, int T, int C, void* stream) {
+    dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+    btc_to_bct_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, T, C);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_cast(const float* in, void* out, long long n, int out_dtype, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n <= 0) return SVC_OK;
+    const unsigned blocks = static_cast<unsigned>(std::min<long long>((n + 255) / 256, kNumSMs * 16));
+    if (out_dtype == SVC_F32)
+        cast_kernel<float><<<blocks, 256, 0, st>>>(in, static_cast<float*>(out), n);
+    else
+        cast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(in, static_cast<__nv_bfloat16*>(out), n);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_reflect_halo(void* buf, long long bstride, long long rstride, int B, int T, int C,
+                                int pad, const int* lens, int dtype, void* stream) {
+    if (pad < 1 || T < pad + 1) {
+        svc_set_error("svc_reflect_halo: need T > pad >= 1");
+        return SVC_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(2 * pad, B);
+    if (dtype == SVC_F32)
+        reflect_halo_kernel<float><<<grid, 128, 0, st>>>(static_cast<float*>(buf), bstride, rstride, T,
+                                                         C, pad, lens);
+    else
+        reflect_halo_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(static_cast<__nv_bfloat16*>(buf),
+                                                                 bstride, rstride, T, C, pad, lens);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_timestep_embedding(const float* t, const float* freqs, float* out, int n, int half,
+                                      void* stream) {
+    if (n < 1) return SVC_OK;
+    timestep_embedding_kernel<<<n, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, freqs, out, n, half);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_set_rows(const float* src, long long src_bstride, float* dst, long long dst_bstride,
+                            int B, int D, void* stream) {
+    if (B < 1) return SVC_OK;
+    set_rows_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(src, src_bstride, dst,
+                                                                     dst_bstride, D);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// error plumbing shared by all translation units
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void svc_set_error(const char* msg) {
+    strncpy(g_err, msg, sizeof(g_err) - 1);
+    g_err[sizeof(g_err) - 1] = 0;
+}
+extern "C" const char* svc_last_error(void) { return g_err; }
+extern "C" int svc_version(void) { return 100; }

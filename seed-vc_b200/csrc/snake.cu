@@ -1,0 +1,245 @@
+// Anti-aliased Snake / SnakeBeta on frames-major (B, L, C) activations, written anew for
+// sm_100a (the reference's own op, anti_alias_activation_cuda.cu:44-179, is not reused).
+//
+// Maths (reference: alias_free_activation/torch/{act,resample,filter}.py,
+// activations.py:107-119), h = 12-tap Kaiser-sinc low-pass:
+//   u[m] = 2 * sum_{k, (m+5-k) even} h[k] * x[clamp((m+5-k)/2, 0, L-1)]      m in [0, 2L)
+//   u[m] = u[m] + inv_b * sin(a * u[m])^2
+//   y[n] = sum_{k=0..11} h[k] * u[clamp(2n+k-5, 0, 2L-1)]                     n in [0, L)
+// For interior outputs, u[2n+5] and u[2n+6] both read x[n .. n+5], so one thread walks along
+// time with a 6-deep x window and a 12-deep u window in registers: 1 shared-memory load, 24 FMA
+// and 2 sin per output.  A block stages a (TL + 10) x CT tile (replicate-clamped rows) in
+// shared memory with coalesced loads; lanes map to channels, so global and shared accesses
+// are contiguous and conflict-free (row stride CT+1 spreads the time-chunks of narrow tiles
+// over the banks).
+#include "common.cuh"
+
+namespace svc {
+
+__constant__ float c_h12[12] = {
+    0.0020289648f, 0.0093894657f, -0.0255434588f, -0.0576573834f, 0.1285725832f, 0.4432097971f,
+    0.4432097971f, 0.1285725832f, -0.0576573834f, -0.0255434588f, 0.0093894657f, 0.0020289648f};
+
+template <bool PRECISE>
+__device__ __forceinline__ float snake_fn(float u, float a, float inv_b) {
+    const float s = PRECISE ? sinf(u * a) : __sinf(u * a);
+    return fmaf(inv_b * s, s, u);
+}
+
+// u at (clamped) upsampled index m, reading x through `xat(l)` with l already clamped
+template <bool PRECISE, typename F>
+__device__ __forceinline__ float up_point(int m, int L, float a, float inv_b, F xat) {
+    m = min(max(m, 0), 2 * L - 1);
+    const int q = m >> 1;
+    float acc = 0.f;
+    if (m & 1) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc = fmaf(c_h12[2 * j], xat(min(max(q + 3 - j, 0), L - 1)), acc);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc = fmaf(c_h12[2 * j + 1], xat(min(max(q + 2 - j, 0), L - 1)), acc);
+    }
+    return snake_fn<PRECISE>(2.0f * acc, a, inv_b);
+}
+
+template <typename TI, typename TO, int CT, int LPT, bool PRECISE>
+__global__ void __launch_bounds__(256) snake_aa_kernel(const TI* __restrict__ x, TO* __restrict__ out,
+                                                       const float* __restrict__ a_p,
+                                                       const float* __restrict__ invb_p, int L, int C) {
+    constexpr int NCHUNK = 256 / CT;
+    constexpr int TL = NCHUNK * LPT;
+    constexpr int ROWS = TL + 10;
+    constexpr int STRIDE = CT + 1;
+    __shared__ float xs[ROWS * STRIDE];
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CT;
+    const int l0 = blockIdx.x * TL;
+    const TI* xb = x + static_cast<long long>(b) * L * C;
+    // stage rows l0-5 .. l0+TL+4, clamped to [0, L-1] (replicate padding of the upsampler)
+    for (int i = threadIdx.x; i < ROWS * CT; i += 256) {
+        const int r = i / CT, c = i % CT;
+        const int l = min(max(l0 - 5 + r, 0), L - 1);
+        float v = 0.f;
+        if (c0 + c < C) v = to_f32<TI>(xb[static_cast<long long>(l) * C + c0 + c]);
+        xs[r * STRIDE + c] = v;
+    }
+    __syncthreads();
+    const int c = threadIdx.x % CT;
+    const int chunk = threadIdx.x / CT;
+    if (c0 + c >= C) return;
+    const int n0 = l0 + chunk * LPT;
+    if (n0 >= L) return;
+    const float a = __ldg(a_p + c0 + c), inv_b = __ldg(invb_p + c0 + c);
+    TO* ob = out + static_cast<long long>(b) * L * C + c0 + c;
+    const float* col = xs + c;
+    // local row of global index l is (l - l0 + 5)
+    const int n_last = min(n0 + LPT, L) - 1;
+    const bool interior = (2 * n0 - 5 >= 0) && (2 * n_last + 6 <= 2 * L - 1) && (n_last == n0 + LPT - 1);
+    if (interior) {
+        float xw[6];   // x[n .. n+5] for the current n
+        float uw[12];  // u[2n-5 .. 2n+6]
+        const int r0 = n0 - l0 + 5;
+        // fill u[2n0-5 .. 2n0+4]: pairs (u[2q'+1], u[2q'+2]) come from x[q'-2 .. q'+3]
+#pragma unroll
+        for (int pz = 0; pz < 5; ++pz) {
+            // pair index pz covers u[2(n0-3+pz)+1], u[2(n0-3+pz)+2]; window x[n0-5+pz .. n0+pz]
+            float e = 0.f, o = 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const float xv = col[(r0 - 5 + pz + 5 - j) * STRIDE];
+                e = fmaf(c_h12[2 * j], xv, e);       // odd index  m = 2q+1, q = n0-3+pz
+                o = fmaf(c_h12[2 * j + 1], xv, o);   // even index m = 2q+2
+            }
+            uw[2 * pz] = snake_fn<PRECISE>(2.0f * e, a, inv_b);
+            uw[2 * pz + 1] = snake_fn<PRECISE>(2.0f * o, a, inv_b);
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) xw[j + 1] = col[(r0 + j) * STRIDE];  // x[n0 .. n0+4] -> slots 1..5
+#pragma unroll
+        for (int i = 0; i < LPT; ++i) {
+            // shift in x[n+5]
+#pragma unroll
+            for (int j = 0; j < 5; ++j) xw[j] = xw[j + 1];
+            xw[5] = col[(r0 + i + 5) * STRIDE];
+            float e = 0.f, o = 0.f;  // u[2n+5] (odd, q=n+2), u[2n+6] (even, q=n+3): x[n+5-j]
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                e = fmaf(c_h12[2 * j], xw[5 - j], e);
+                o = fmaf(c_h12[2 * j + 1], xw[5 - j], o);
+            }
+            uw[10] = snake_fn<PRECISE>(2.0f * e, a, inv_b);
+            uw[11] = snake_fn<PRECISE>(2.0f * o, a, inv_b);
+            float y = 0.f;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) y = fmaf(c_h12[k], uw[k], y);
+            ob[static_cast<long long>(n0 + i) * C] = from_f32<TO>(y);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) uw[k] = uw[k + 2];
+        }
+    } else {
+        auto xat = [&](int l) { return col[(l - l0 + 5) * STRIDE]; };
+        for (int n = n0; n <= n_last; ++n) {
+            float y = 0.f;
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                y = fmaf(c_h12[k], up_point<PRECISE>(2 * n + k - 5, L, a, inv_b, xat), y);
+            ob[static_cast<long long>(n) * C] = from_f32<TO>(y);
+        }
+    }
+}
+
+// activation_post + conv_post (C -> 1, k taps, zero padding) + clamp / tanh.
+// Reference: modules/bigvgan/bigvgan.py:377-384.
+template <bool PRECISE>
+__global__ void __launch_bounds__(256) snake_conv_post_kernel(
+    const float* __restrict__ x, const float* __restrict__ a_p, const float* __restrict__ invb_p,
+    const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out, int L, int C,
+    int ksize, int use_tanh) {
+    constexpr int TL = 256;
+    extern __shared__ float sm[];
+    const int half = ksize / 2;
+    const int xr = TL + 2 * half + 10;        // x rows staged
+    const int yr = TL + 2 * half;             // activation rows needed
+    float* xs = sm;                           // xr * (C+1)
+    float* ys = xs + xr * (C + 1);            // yr * (C+1)
+    float* ws = ys + yr * (C + 1);            // ksize * C
+    const int b = blockIdx.y;
+    const int l0 = blockIdx.x * TL;
+    const float* xb = x + static_cast<long long>(b) * L * C;
+    for (int i = threadIdx.x; i < xr * C; i += 256) {
+        const int r = i / C, c = i % C;
+        const int l = min(max(l0 - half - 5 + r, 0), L - 1);
+        xs[r * (C + 1) + c] = xb[static_cast<long long>(l) * C + c];
+    }
+    for (int i = threadIdx.x; i < ksize * C; i += 256) ws[i] = w[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < yr * C; i += 256) {
+        const int r = i / C, c = i % C;
+        const int n = l0 - half + r;
+        float y = 0.f;
+        if (n >= 0 && n < L) {
+            const float a = a_p[c], inv_b = invb_p[c];
+            auto xat = [&](int l) { return xs[(l - (l0 - half - 5)) * (C + 1) + c]; };
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                y = fmaf(c_h12[k], up_point<PRECISE>(2 * n + k - 5, L, a, inv_b, xat), y);
+        }
+        ys[r * (C + 1) + c] = y;
+    }
+    __syncthreads();
+    const int n = l0 + threadIdx.x;
+    if (n < L) {
+        float acc = bias != nullptr ? bias[0] : 0.f;
+        for (int k = 0; k < ksize; ++k)
+            for (int c = 0; c < C; ++c) acc = fmaf(ws[k * C + c], ys[(threadIdx.x + k) * (C + 1) + c], acc);
+        acc = use_tanh ? tanhf(acc) : fminf(fmaxf(acc, -1.0f), 1.0f);
+        out[static_cast<long long>(b) * L + n] = acc;
+    }
+}
+
+template <typename TI, typename TO, bool PRECISE>
+static int launch_snake(const void* x, void* out, const float* a, const float* inv_b, int B, int L,
+                        int C, cudaStream_t st) {
+    const TI* xi = static_cast<const TI*>(x);
+    TO* o = static_cast<TO*>(out);
+    if (C % 32 == 0 || C > 64) {
+        constexpr int CT = 32, LPT = 16, TL = (256 / CT) * LPT;
+        dim3 grid((L + TL - 1) / TL, (C + CT - 1) / CT, B);
+        snake_aa_kernel<TI, TO, CT, LPT, PRECISE><<<grid, 256, 0, st>>>(xi, o, a, inv_b, L, C);
+    } else if (C % 16 == 0) {
+        constexpr int CT = 16, LPT = 16, TL = (256 / CT) * LPT;
+        dim3 grid((L + TL - 1) / TL, (C + CT - 1) / CT, B);
+        snake_aa_kernel<TI, TO, CT, LPT, PRECISE><<<grid, 256, 0, st>>>(xi, o, a, inv_b, L, C);
+    } else {
+        constexpr int CT = 8, LPT = 8, TL = (256 / CT) * LPT;
+        dim3 grid((L + TL - 1) / TL, (C + CT - 1) / CT, B);
+        snake_aa_kernel<TI, TO, CT, LPT, PRECISE><<<grid, 256, 0, st>>>(xi, o, a, inv_b, L, C);
+    }
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+}  // namespace svc
+
+using namespace svc;
+
+extern "C" int svc_snake_aa(const void* x, int x_dtype, void* out, int out_dtype, const float* a,
+                            const float* inv_b, int B, int L, int C, int precise, void* stream) {
+    if (B < 1 || L < 1 || C < 1 || B > 65535) {
+        svc_set_error("svc_snake_aa: bad shape");
+        return SVC_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define SNAKE_DISPATCH(TI, TO)                                                         \
+    return precise ? launch_snake<TI, TO, true>(x, out, a, inv_b, B, L, C, st)         \
+                   : launch_snake<TI, TO, false>(x, out, a, inv_b, B, L, C, st)
+    if (x_dtype == SVC_F32 && out_dtype == SVC_F32) { SNAKE_DISPATCH(float, float); }
+    if (x_dtype == SVC_F32 && out_dtype == SVC_BF16) { SNAKE_DISPATCH(float, __nv_bfloat16); }
+    if (x_dtype == SVC_BF16 && out_dtype == SVC_BF16) { SNAKE_DISPATCH(__nv_bfloat16, __nv_bfloat16); }
+    if (x_dtype == SVC_BF16 && out_dtype == SVC_F32) { SNAKE_DISPATCH(__nv_bfloat16, float); }
+#undef SNAKE_DISPATCH
+    svc_set_error("svc_snake_aa: unsupported dtype");
+    return SVC_ERR_UNSUPPORTED;
+}
+
+extern "C" int svc_snake_conv_post(const float* x, const float* a, const float* inv_b, const float* w,
+                                   const float* bias, float* out, int B, int L, int C, int ksize,
+                                   int use_tanh, int precise, void* stream) {
+    if (B < 1 || L < 1 || C < 1 || C > 64 || ksize < 1 || ksize > 15 || (ksize % 2) == 0) {
+        svc_set_error("svc_snake_conv_post: C <= 64 and odd ksize <= 15 required");
+        return SVC_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int half = ksize / 2;
+    const int smem = ((256 + 2 * half + 10) + (256 + 2 * half)) * (C + 1) * 4 + ksize * C * 4;
+    dim3 grid((L + 255) / 256, B);
+    if (precise) {
+        cudaFuncSetAttribute(snake_conv_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        snake_conv_post_kernel<true><<<grid, 256, smem, st>>>(x, a, inv_b, w, bias, out, L, C, ksize, use_tanh);
+    } else {
+        cudaFuncSetAttribute(snake_conv_post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        snake_conv_post_kernel<false><<<grid, 256, smem, st>>>(x, a, inv_b, w, bias, out, L, C, ksize, use_tanh);
+    }
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}

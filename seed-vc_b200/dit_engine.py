@@ -1,0 +1,506 @@
+"""Host-side orchestration of the DiT velocity estimator on the sm_100a kernels.
+
+This is the part of the hot path the reference runs as ~1000 small PyTorch ops per
+Euler step.  Here one solve is:
+
+``begin``  - once per ``solve_euler`` call: everything that does not depend on ``x``
+             (SURVEY App. B-3): ``cond_projection(mu)``, the prompt / content / style
+             columns of ``cond_x_merge_linear``, the null-branch constants, the style
+             token, and - for *all* Euler steps at once - the timestep MLPs, every
+             AdaLN projection, the WaveNet ``cond_layer`` and the FinalLayer modulation.
+``step``   - per Euler step: the ``x`` columns of the merge GEMM (K = n_mels), the
+             transformer layers, the head; returns the velocity of every CFG branch.
+
+Activations are frames-major ``(rows, T', D)``; residual streams are fp32, GEMM operands
+are in the operand dtype (bf16 on tensor cores / fp32 in fp32 mode).  All arithmetic is
+in ``libseedvc_b200.so``; torch only allocates.
+
+Reference: modules/diffusion_transformer.py:77-147 (Transformer), :150-191 (block),
+:194-260 (attention), :263-271 (FFN), :30-48/:274-285 (AdaLN/RMSNorm), :388-405 (FinalLayer),
+:486-537 (DiT.forward); modules/wavenet.py:138-166; modules/encodec.py:212-228;
+v2: modules/v2/dit_model.py:82-143, modules/v2/dit_wrapper.py:114-152.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from ._lib import ACT_NONE, ACT_ROPE, ACT_SILU, ACT_SWIGLU_PAIR, ACT_TANH_SIG_PAIR
+
+
+@dataclass
+class DiTSpec:
+    """Static description of one estimator (v1 or v2)."""
+    version: int          # 1 or 2
+    D: int
+    H: int
+    L: int
+    C: int                # mel bins
+    content_dim: int
+    style_dim: int
+    time_as_token: bool
+    style_as_token: bool
+    style_in_merge: bool  # v1 style_condition and not style_as_token
+    uvit: bool
+    long_skip: bool
+    head: str             # "mlp" | "wavenet"
+    Dw: int = 0
+    wn_layers: int = 0
+    wn_kernel: int = 5
+    prefix: str = "estimator."
+
+    @property
+    def I(self):
+        n = int(2 * 4 * self.D / 3)
+        return n if n % 256 == 0 else n + 256 - (n % 256)
+
+    @property
+    def ntok(self):
+        return int(self.time_as_token) + int(self.style_as_token)
+
+
+def _fold_wn(sd, prefix):
+    """w = g * v / ||v|| over all dims but 0 (torch weight_norm dim=0)."""
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"].float()
+    v, g = sd[prefix + ".weight_v"].float(), sd[prefix + ".weight_g"].float()
+    n = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+    return g * v / n
+
+
+def _interleave_rows(a, b):
+    """rows a0,b0,a1,b1,... (pair activations read adjacent accumulator columns)."""
+    return torch.stack([a, b], dim=1).reshape(a.shape[0] * 2, *a.shape[1:])
+
+
+def rope_table(n_pos, head_dim=64, base=10000.0, bf16_round=False):
+    """cos/sin table exactly as the reference builds it
+    (modules/diffusion_transformer.py:288-297; v2 rounds it to bf16)."""
+    freqs = 1.0 / (base ** (torch.arange(0, head_dim, 2)[: head_dim // 2].float() / head_dim))
+    ang = torch.outer(torch.arange(n_pos), freqs)
+    fc = torch.polar(torch.ones_like(ang), ang)
+    tab = torch.stack([fc.real, fc.imag], dim=-1)
+    if bf16_round:
+        tab = tab.to(torch.bfloat16).float()
+    return tab.contiguous()
+
+
+class DiTEngine:
+    def __init__(self, spec: DiTSpec, ops):
+        self.spec = spec
+        self.ops = ops
+        self.w = None
+        self.rope = None
+        self.max_pos = 0
+
+    # ------------------------------------------------------------------ weights
+    def load_weights(self, sd, device):
+        """Fold weight-norm, fuse / interleave / split and cast the reference state_dict."""
+        sp, ops = self.spec, self.ops
+        p = sp.prefix
+        od = ops.op_dtype
+        D, L, C = sp.D, sp.L, sp.C
+
+        def dev(t, dtype=None):
+            return t.detach().to(device=device, dtype=dtype or torch.float32).contiguous()
+
+        w = {}
+        layers = []
+        ada_w, ada_b = [], []          # stacked AdaLN projections, fp32
+        ada_index = {}
+
+        def add_ada(name, weight, bias, one_plus_rows=()):
+            bias = bias.clone().float()
+            for lo, hi in one_plus_rows:      # "(1 + scale)" folded into the bias
+                bias[lo:hi] += 1.0
+            ada_index[name] = (sum(x.shape[0] for x in ada_w), weight.shape[0])
+            ada_w.append(weight.float())
+            ada_b.append(bias)
+
+        for i in range(L):
+            lp = f"{p}transformer.layers.{i}."
+            lw = {
+                "wqkv": dev(sd[lp + "attention.wqkv.weight"], od),
+                "wo": dev(sd[lp + "attention.wo.weight"], od),
+                "w13": dev(_interleave_rows(sd[lp + "feed_forward.w1.weight"].float(),
+                                            sd[lp + "feed_forward.w3.weight"].float()), od),
+                "w2": dev(sd[lp + "feed_forward.w2.weight"], od),
+            }
+            if sp.version == 1:
+                lw["g_attn"] = dev(sd[lp + "attention_norm.norm.weight"])
+                lw["g_ffn"] = dev(sd[lp + "ffn_norm.norm.weight"])
+                if not sp.time_as_token:
+                    add_ada(f"attn{i}", sd[lp + "attention_norm.project_layer.weight"],
+                            sd[lp + "attention_norm.project_layer.bias"])
+                    add_ada(f"ffn{i}", sd[lp + "ffn_norm.project_layer.weight"],
+                            sd[lp + "ffn_norm.project_layer.bias"])
+                if sp.uvit and i > L // 2:
+                    sk = dev(sd[lp + "skip_in_linear.weight"], od)
+                    lw["skip_w"] = sk
+                    lw["skip_b"] = dev(sd[lp + "skip_in_linear.bias"])
+            else:
+                lw["g_attn"] = dev(sd[lp + "attention_norm.norm.weight"])
+                lw["g_ffn"] = dev(sd[lp + "ffn_norm.weight"])
+                # chunks: shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+                add_ada(f"blk{i}", sd[lp + "attention_norm.linear.weight"],
+                        sd[lp + "attention_norm.linear.bias"],
+                        one_plus_rows=((D, 2 * D), (4 * D, 5 * D)))
+            layers.append(lw)
+        w["layers"] = layers
+        w["g_final"] = dev(sd[p + "transformer.norm.norm.weight"])
+        if sp.version == 1:
+            add_ada("final", sd[p + "transformer.norm.project_layer.weight"],
+                    sd[p + "transformer.norm.project_layer.bias"])
+        else:  # chunks: scale, shift (dit_model.py:50-53)
+            add_ada("final", sd[p + "transformer.norm.linear.weight"],
+                    sd[p + "transformer.norm.linear.bias"], one_plus_rows=((0, D),))
+        if sp.head == "wavenet":  # FinalLayer: shift, scale = chunk(Linear(SiLU(t1)))
+            Dw = sp.Dw
+            add_ada("fl", sd[p + "final_layer.adaLN_modulation.1.weight"],
+                    sd[p + "final_layer.adaLN_modulation.1.bias"], one_plus_rows=((Dw, 2 * Dw),))
+        w["ada_w"] = dev(torch.cat(ada_w, 0))
+        w["ada_b"] = dev(torch.cat(ada_b, 0))
+        w["ada_index"] = ada_index
+        # which rows of the stacked projection take SiLU(t1) instead of t1
+        w["ada_silu"] = sp.version == 2
+
+        for name in ("t_embedder",) + (("t_embedder2",) if sp.head == "wavenet" else ()):
+            w[name] = {
+                "w0": dev(sd[f"{p}{name}.mlp.0.weight"]), "b0": dev(sd[f"{p}{name}.mlp.0.bias"]),
+                "w2": dev(sd[f"{p}{name}.mlp.2.weight"]), "b2": dev(sd[f"{p}{name}.mlp.2.bias"]),
+            }
+        half = 128
+        w["freqs"] = dev(torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half))
+
+        w["cond_w"] = dev(sd[p + "cond_projection.weight"], od)
+        w["cond_b"] = dev(sd[p + "cond_projection.bias"])
+        mw = sd[p + "cond_x_merge_linear.weight"].float()
+        w["merge_w"] = dev(mw, od)                       # column blocks are taken as views
+        w["merge_b"] = dev(sd[p + "cond_x_merge_linear.bias"])
+        # null-branch constant of the content columns: W_c @ b_cond (fp32, exact)
+        Wc = mw[:, 2 * C:2 * C + D]
+        w["merge_null_c"] = dev(Wc @ sd[p + "cond_projection.bias"].float())
+        if sp.style_in_merge:
+            w["merge_ws"] = dev(mw[:, 2 * C + D:2 * C + D + sp.style_dim])   # fp32 (B rows only)
+        if sp.style_as_token or sp.version == 2:
+            w["style_in_w"] = dev(sd[p + "style_in.weight"])
+            w["style_in_b"] = dev(sd[p + "style_in.bias"])
+        if sp.long_skip:
+            w["lskip_w"] = dev(sd[p + "skip_linear.weight"], od)
+            w["lskip_b"] = dev(sd[p + "skip_linear.bias"])
+        if sp.head == "mlp":
+            w["mlp0_w"] = dev(sd[p + "final_mlp.0.weight"], od)
+            w["mlp0_b"] = dev(sd[p + "final_mlp.0.bias"])
+            w["mlp2_w"] = dev(sd[p + "final_mlp.2.weight"], od)
+            w["mlp2_b"] = dev(sd[p + "final_mlp.2.bias"])
+        else:
+            Dw, nl, ks = sp.Dw, sp.wn_layers, sp.wn_kernel
+            w["conv1_w"] = dev(sd[p + "conv1.weight"], od)
+            w["conv1_b"] = dev(sd[p + "conv1.bias"])
+            w["resp_w"] = dev(sd[p + "res_projection.weight"], od)
+            w["resp_b"] = dev(sd[p + "res_projection.bias"])
+            w["conv2_w"] = dev(sd[p + "conv2.weight"].float().reshape(C, Dw), od)
+            w["conv2_b"] = dev(sd[p + "conv2.bias"])
+            w["fl_w"] = dev(_fold_wn(sd, p + "final_layer.linear"), od)
+            w["fl_b"] = dev(sd[p + "final_layer.linear.bias"])
+            cw = _fold_wn(sd, p + "wavenet.cond_layer.conv.conv").reshape(2 * Dw * nl, Dw)
+            cb = sd[p + "wavenet.cond_layer.conv.conv.bias"].float()
+            cws, cbs, wn = [], [], []
+            for l in range(nl):
+                wi = _fold_wn(sd, f"{p}wavenet.in_layers.{l}.conv.conv")      # (2Dw, Dw, k)
+                bi = sd[f"{p}wavenet.in_layers.{l}.conv.conv.bias"].float()
+                wi = _interleave_rows(wi[:Dw], wi[Dw:])                        # tanh/sigmoid pairs
+                bi = _interleave_rows(bi[:Dw], bi[Dw:])
+                cl = cw[l * 2 * Dw:(l + 1) * 2 * Dw]
+                cbl = cb[l * 2 * Dw:(l + 1) * 2 * Dw]
+                cws.append(_interleave_rows(cl[:Dw], cl[Dw:]))
+                cbs.append(_interleave_rows(cbl[:Dw], cbl[Dw:]) + bi)           # conv bias folded in
+                wr = _fold_wn(sd, f"{p}wavenet.res_skip_layers.{l}.conv.conv")
+                wr = wr.reshape(wr.shape[0], Dw)
+                br = sd[f"{p}wavenet.res_skip_layers.{l}.conv.conv.bias"].float()
+                wn.append({
+                    "in_w": dev(wi.permute(2, 0, 1), od),                      # (k, 2Dw, Dw)
+                    "rs_w": dev(wr, od), "rs_b": dev(br),
+                    "rs_b_res": dev(br[:Dw]), "rs_b_skip": dev(br[Dw:]),
+                })
+            w["wn"] = wn
+            w["wn_cond_w"] = dev(torch.cat(cws, 0))                            # (nl*2Dw, Dw) fp32
+            w["wn_cond_b"] = dev(torch.cat(cbs, 0))
+        self.w = w
+
+    def setup_rope(self, n_pos, device):
+        if self.rope is None or self.max_pos < n_pos:
+            self.rope = rope_table(n_pos, bf16_round=self.spec.version == 2).to(device)
+            self.max_pos = n_pos
+
+    # ------------------------------------------------------------------ per-solve precompute
+    def begin(self, branches, prompt_op, mu, style, x_lens, t_values):
+        """branches: list of (use_prompt, use_style, use_mu) flags, one per CFG branch.
+
+        prompt_op: (B, T, C) operand dtype (zeros outside the prompt); mu: (B, T, cd) fp32;
+        style: (B, style_dim) fp32; x_lens: (B,) int; t_values: (N,) fp32 CPU tensor.
+        """
+        sp, ops, w = self.spec, self.ops, self.w
+        dev = mu.device
+        B, T, _ = mu.shape
+        D, C, L = sp.D, sp.C, sp.L
+        nb = len(branches)
+        ntok = sp.ntok
+        Tq = T + ntok
+        N = int(t_values.numel())
+        self.setup_rope(max(Tq, 1), dev)
+        st = {"B": B, "T": T, "Tq": Tq, "nb": nb, "N": N, "branches": branches}
+        f32 = torch.float32
+
+        # ---- time conditioning for every step at once (rows = steps) -------------------
+        tdev = t_values.to(device=dev, dtype=f32).contiguous()
+
+        def t_embed(name):
+            tw = w[name]
+            Dh = tw["w0"].shape[0]
+            feat = torch.empty(N, 256, dtype=f32, device=dev)
+            ops.timestep_embedding(tdev, w["freqs"], feat)
+            h0 = torch.empty(1, N, Dh, dtype=f32, device=dev)
+            ops.gemm([(feat.view(1, N, 256), 0, tw["w0"])], Dh, B=1, T=N, bias=tw["b0"],
+                     act=ACT_SILU, out_f32=h0, f32=True)
+            t1 = torch.empty(1, N, Dh, dtype=f32, device=dev)
+            ops.gemm([(h0, 0, tw["w2"])], Dh, B=1, T=N, bias=tw["b2"], out_f32=t1, f32=True)
+            t1s = torch.empty(1, N, Dh, dtype=f32, device=dev)
+            ops.gemm([(h0, 0, tw["w2"])], Dh, B=1, T=N, bias=tw["b2"], act=ACT_SILU, out_f32=t1s,
+                     f32=True)
+            return t1, t1s
+
+        t1, t1s = t_embed("t_embedder")
+        st["t1"] = t1[0]                                   # (N, D)
+        n_ada = w["ada_w"].shape[0]
+        ada = torch.empty(1, N, n_ada, dtype=f32, device=dev)
+        if sp.version == 2:
+            ops.gemm([(t1s, 0, w["ada_w"])], n_ada, B=1, T=N, bias=w["ada_b"], out_f32=ada, f32=True)
+        else:
+            # v1: AdaLN projections take t1; the FinalLayer modulation takes SiLU(t1)
+            if sp.head == "wavenet":
+                lo, n_fl = w["ada_index"]["fl"]
+                ops.gemm([(t1, 0, w["ada_w"][:lo])], lo, B=1, T=N, bias=w["ada_b"][:lo],
+                         out_f32=ada[:, :, :lo], f32=True)
+                ops.gemm([(t1s, 0, w["ada_w"][lo:])], n_fl, B=1, T=N, bias=w["ada_b"][lo:],
+                         out_f32=ada[:, :, lo:], f32=True)
+            else:
+                ops.gemm([(t1, 0, w["ada_w"])], n_ada, B=1, T=N, bias=w["ada_b"], out_f32=ada,
+                         f32=True)
+        st["ada"] = ada[0]                                 # (N, n_ada)
+        if sp.head == "wavenet":
+            t2, _ = t_embed("t_embedder2")
+            ng = w["wn_cond_w"].shape[0]
+            g = torch.empty(1, N, ng, dtype=f32, device=dev)
+            ops.gemm([(t2, 0, w["wn_cond_w"])], ng, B=1, T=N, bias=w["wn_cond_b"], out_f32=g, f32=True)
+            st["wn_g"] = g[0]                              # (N, nl*2Dw), conv bias included
+
+        # ---- step-invariant part of cond_x_merge_linear ----------------------------------
+        mu_op = ops.empty(B, T, sp.content_dim, device=dev)
+        ops.cast(mu.contiguous(), mu_op)
+        cond_op = ops.empty(B, T, D, device=dev)
+        ops.gemm([(mu_op, 0, w["cond_w"])], D, B=B, T=T, bias=w["cond_b"], out_op=cond_op)
+        mw = w["merge_w"]
+        Wx, Wp, Wc = mw[:, :C], mw[:, C:2 * C], mw[:, 2 * C:2 * C + D]
+        st["Wx"] = Wx
+        style_rb = None
+        if sp.style_in_merge:
+            style_rb = torch.empty(1, B, D, dtype=f32, device=dev)   # style @ Ws^T + b_merge
+            ops.gemm([(style.contiguous().view(1, B, sp.style_dim), 0, w["merge_ws"])], D, B=1, T=B,
+                     bias=w["merge_b"], out_f32=style_rb, f32=True)
+        null_vec = (w["merge_null_c"] + w["merge_b"]).contiguous()   # tiny host-side prep
+        consts = []
+        cache = {}
+        for (use_p, use_s, use_m) in branches:
+            key = (use_p, use_s and sp.style_in_merge, use_m)
+            if key in cache:
+                consts.append(cache[key])
+                continue
+            segs = []
+            if use_p:
+                segs.append((prompt_op, 0, Wp))
+            if use_m:
+                segs.append((cond_op, 0, Wc))
+            if not segs:
+                entry = ("vec", null_vec if not key[1] else None)
+                if key[1]:   # style without prompt/content: not produced by any reference branch
+                    raise NotImplementedError("style-only CFG branch")
+            else:
+                Hk = torch.empty(B, T, D, dtype=f32, device=dev)
+                rb, bias = None, w["merge_b"]
+                if key[1]:
+                    rb, bias = style_rb[0], None
+                if not use_m:   # content columns see cond_projection(0) = b_cond
+                    bias = (w["merge_null_c"] + (w["merge_b"] if bias is not None else 0)).contiguous()
+                ops.gemm(segs, D, B=B, T=T, bias=bias, rowbias=rb, out_f32=Hk)
+                entry = ("mat", Hk)
+            cache[key] = entry
+            consts.append(entry)
+        st["consts"] = consts
+
+        # ---- tokens ------------------------------------------------------------------------
+        if sp.style_as_token:
+            tok = torch.empty(1, B, D, dtype=f32, device=dev)
+            ops.gemm([(style.contiguous().view(1, B, sp.style_dim), 0, w["style_in_w"])], D, B=1, T=B,
+                     bias=w["style_in_b"], out_f32=tok, f32=True)
+            st["style_tok"] = tok[0]                            # (B, D)
+            st["style_tok_null"] = w["style_in_b"].view(1, D)   # style_in(0)
+        kv = (x_lens.to(device=dev, dtype=torch.int32) + ntok).repeat(nb).contiguous()
+        st["kv_len"] = kv
+        st["x_lens"] = x_lens.to(device=dev, dtype=torch.int32).contiguous()
+
+        # ---- work buffers ------------------------------------------------------------------
+        R = nb * B
+        od = ops.op_dtype
+        st["h"] = torch.empty(R, Tq, D, dtype=f32, device=dev)
+        st["xn"] = torch.empty(R, Tq, D, dtype=od, device=dev)
+        st["qkv"] = torch.empty(R, Tq, 3 * D, dtype=od, device=dev)
+        st["att"] = torch.empty(R, Tq, D, dtype=od, device=dev)
+        st["ff"] = torch.empty(R, Tq, sp.I, dtype=od, device=dev)
+        st["h_op"] = torch.empty(R, Tq, D, dtype=od, device=dev)
+        n_skip = L // 2 if sp.uvit else 0
+        st["skips"] = [torch.empty(R, Tq, D, dtype=od, device=dev) for _ in range(n_skip)]
+        st["v"] = torch.empty(R, T, C, dtype=f32, device=dev)
+        if sp.long_skip:
+            st["x_res"] = torch.empty(R, T, D, dtype=od, device=dev)
+        if sp.head == "mlp":
+            st["y"] = torch.empty(R, T, D, dtype=od, device=dev)
+        else:
+            Dw, pad = sp.Dw, (sp.wn_kernel - 1) // 2
+            st["xw"] = torch.empty(R, T, Dw, dtype=f32, device=dev)
+            st["xw_op"] = torch.zeros(R, T + 2 * pad, Dw, dtype=od, device=dev)
+            st["acts"] = torch.empty(R, T, Dw, dtype=od, device=dev)
+            st["wn_out"] = torch.empty(R, T, Dw, dtype=f32, device=dev)
+            st["ln"] = torch.empty(R, T, Dw, dtype=od, device=dev)
+            st["y"] = torch.empty(R, T, Dw, dtype=od, device=dev)
+            st["wn_lens"] = st["x_lens"].repeat(nb).contiguous()
+        self.st = st
+        return st
+
+    # ------------------------------------------------------------------ one estimator call
+    def _ada(self, s, name):
+        lo, n = self.w["ada_index"][name]
+        return self.st["ada"][s, lo:lo + n]
+
+    def step(self, s, x_op):
+        """Velocity of every branch at step ``s``: (nb*B, T, C) fp32.  x_op: (B, T, C)."""
+        sp, ops, w, st = self.spec, self.ops, self.w, self.st
+        B, T, Tq, nb = st["B"], st["T"], st["Tq"], st["nb"]
+        D, C, L, H = sp.D, sp.C, sp.L, sp.H
+        ntok = sp.ntok
+        R = nb * B
+        h, xn, qkv, att, ff = st["h"], st["xn"], st["qkv"], st["att"], st["ff"]
+        hb = h[:, ntok:, :]                                   # frame rows of the hidden state
+
+        # ---- input assembly: x columns of cond_x_merge_linear + hoisted constants ----------
+        for k, (kind, val) in enumerate(st["consts"]):
+            out = hb[k * B:(k + 1) * B]
+            if kind == "mat":
+                ops.gemm([(x_op, 0, st["Wx"])], D, B=B, T=T, res=val, out_f32=out)
+            else:
+                ops.gemm([(x_op, 0, st["Wx"])], D, B=B, T=T, bias=val, out_f32=out)
+        if sp.time_as_token:
+            ops.set_rows(st["t1"][s:s + 1], h[:, 0, :])
+        if sp.style_as_token:
+            r = int(sp.time_as_token)
+            for k, (use_p, use_s, use_m) in enumerate(st["branches"]):
+                src = st["style_tok"] if use_s else st["style_tok_null"]
+                ops.set_rows(src, h[k * B:(k + 1) * B, r, :])
+
+        rope = (self.rope, 2 * D, 0, D, 0.125)
+        emit = set(range(L // 2)) if sp.uvit else set()
+        recv = set(range(L // 2 + 1, L)) if sp.uvit else set()
+        skips = []
+        skip_bufs = list(st["skips"])
+        for i in range(L):
+            lw = w["layers"][i]
+            if i in recv:
+                skip = skips.pop()
+                ops.gemm([(st["h_op"], 0, lw["skip_w"][:, :D]), (skip, 0, lw["skip_w"][:, D:])], D,
+                         B=R, T=Tq, bias=lw["skip_b"], out_f32=h)
+            # ---- attention --------------------------------------------------------------
+            if sp.version == 1:
+                if sp.time_as_token:
+                    ops.norm_mod(h, xn, gamma=lw["g_attn"])
+                else:
+                    a = self._ada(s, f"attn{i}")
+                    ops.norm_mod(h, xn, gamma=lw["g_attn"], mul=a[:D], add=a[D:])
+                gate_a = gate_m = None
+            else:
+                a = self._ada(s, f"blk{i}")     # shift, 1+scale, gate, shift, 1+scale, gate
+                ops.norm_mod(h, xn, gamma=lw["g_attn"], mul=a[D:2 * D], add=a[:D])
+                gate_a = a[2 * D:3 * D].view(1, D).expand(R, D)
+                gate_m = a[5 * D:6 * D].view(1, D).expand(R, D)
+            ops.gemm([(xn, 0, lw["wqkv"])], 3 * D, B=R, T=Tq, act=ACT_ROPE, rope=rope, out_op=qkv)
+            ops.attention(qkv, att, H, st["kv_len"])
+            ops.gemm([(att, 0, lw["wo"])], D, B=R, T=Tq, gate=gate_a, res=h, out_f32=h)
+            # ---- feed-forward -----------------------------------------------------------
+            if sp.version == 1:
+                if sp.time_as_token:
+                    ops.norm_mod(h, xn, gamma=lw["g_ffn"])
+                else:
+                    a = self._ada(s, f"ffn{i}")
+                    ops.norm_mod(h, xn, gamma=lw["g_ffn"], mul=a[:D], add=a[D:])
+            else:
+                ops.norm_mod(h, xn, gamma=lw["g_ffn"], mul=a[4 * D:5 * D], add=a[3 * D:4 * D])
+            ops.gemm([(xn, 0, lw["w13"])], 2 * sp.I, B=R, T=Tq, act=ACT_SWIGLU_PAIR, out_op=ff)
+            out_op = None
+            if i in emit:
+                out_op = skip_bufs.pop(0)
+                skips.append(out_op)
+            elif (i + 1) in recv:
+                out_op = st["h_op"]
+            ops.gemm([(ff, 0, lw["w2"])], D, B=R, T=Tq, gate=gate_m, res=h, out_f32=h, out_op=out_op)
+        # ---- final norm (uses c even when time is a token, diffusion_transformer.py:142) ----
+        a = self._ada(s, "final")
+        if sp.version == 1:
+            ops.norm_mod(h, xn, gamma=w["g_final"], mul=a[:D], add=a[D:])
+        else:
+            ops.norm_mod(h, xn, gamma=w["g_final"], mul=a[:D], add=a[D:])   # (1+scale), shift
+        xf = xn[:, ntok:, :]
+        v = st["v"]
+        if sp.long_skip:     # skip_linear(cat[x_res, x]) without the concat (:524-525)
+            lw_, lb_ = w["lskip_w"], w["lskip_b"]
+            x_res = st["x_res"]
+            for k in range(nb):
+                sl = slice(k * B, (k + 1) * B)
+                ops.gemm([(xf[sl], 0, lw_[:, :D]), (x_op, 0, lw_[:, D:D + C])], D, B=B, T=T, bias=lb_,
+                         out_op=x_res[sl])
+            xr = x_res
+        else:
+            xr = xf
+        if sp.head == "mlp":
+            y = st["y"]
+            ops.gemm([(xr, 0, w["mlp0_w"])], D, B=R, T=T, bias=w["mlp0_b"], act=ACT_SILU, out_op=y)
+            ops.gemm([(y, 0, w["mlp2_w"])], C, B=R, T=T, bias=w["mlp2_b"], out_f32=v)
+            return v
+        # ---- WaveNet head -------------------------------------------------------------------
+        Dw, nl, ks = sp.Dw, sp.wn_layers, sp.wn_kernel
+        pad = (ks - 1) // 2
+        xw, xw_op, acts, wn_out = st["xw"], st["xw_op"], st["acts"], st["wn_out"]
+        body = xw_op[:, pad:pad + T, :]
+        ops.gemm([(xr, 0, w["conv1_w"])], Dw, B=R, T=T, bias=w["conv1_b"], out_f32=xw, out_op=body)
+        ops.reflect_halo(xw_op, T, pad, st["wn_lens"])
+        ops.gemm([(xr, 0, w["resp_w"])], Dw, B=R, T=T, bias=w["resp_b"], out_f32=wn_out)
+        g_all = st["wn_g"][s]
+        for l in range(nl):
+            wl = w["wn"][l]
+            g_l = g_all[l * 2 * Dw:(l + 1) * 2 * Dw].view(1, 2 * Dw).expand(R, 2 * Dw)
+            segs = [(xw_op, j, wl["in_w"][j]) for j in range(ks)]
+            ops.gemm(segs, 2 * Dw, B=R, T=T, rowbias=g_l, act=ACT_TANH_SIG_PAIR, out_op=acts)
+            if l < nl - 1:
+                ops.gemm([(acts, 0, wl["rs_w"][:Dw])], Dw, B=R, T=T, bias=wl["rs_b_res"],
+                         res=xw, out_f32=xw, out_op=body)
+                ops.reflect_halo(xw_op, T, pad, st["wn_lens"])
+                ops.gemm([(acts, 0, wl["rs_w"][Dw:])], Dw, B=R, T=T, bias=wl["rs_b_skip"],
+                         accumulate=True, out_f32=wn_out)
+            else:
+                ops.gemm([(acts, 0, wl["rs_w"])], Dw, B=R, T=T, bias=wl["rs_b"], accumulate=True,
+                         out_f32=wn_out)
+        a = self._ada(s, "fl")                                   # shift, 1+scale
+        ops.norm_mod(wn_out, st["ln"], mul=a[Dw:], add=a[:Dw], eps=1e-6, mode=1)
+        ops.gemm([(st["ln"], 0, w["fl_w"])], Dw, B=R, T=T, bias=w["fl_b"], out_op=st["y"])
+        ops.gemm([(st["y"], 0, w["conv2_w"])], C, B=R, T=T, bias=w["conv2_b"], out_f32=v)
+        return v

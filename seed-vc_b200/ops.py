@@ -1,0 +1,245 @@
+"""Tensor-level wrappers over the C ABI (``include/seedvc_b200.h``).
+
+PyTorch is used only for device memory and the current stream; every method
+hands raw pointers, sizes and strides to ``libseedvc_b200.so``.  ``Ops`` refuses
+non-CUDA tensors: there is no CPU path.
+
+``mode``: ``"bf16"`` (bf16 operands on tcgen05 tensor cores, fp32 accumulate,
+fp32 residual streams) or ``"fp32"`` (fp32 operands, FFMA kernels).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_ROPE, BACKEND_AUTO, BACKEND_SIMT, SVC_BF16, SVC_F32, GemmDesc,
+                   check)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class Ops:
+    def __init__(self, mode: str = "bf16", force_simt: bool = False):
+        if mode not in ("bf16", "fp32"):
+            raise ValueError("mode must be 'bf16' or 'fp32'")
+        self.lib = _lib.load_library()
+        self.mode = mode
+        self.op_dtype = torch.bfloat16 if mode == "bf16" else torch.float32
+        self.op_code = SVC_BF16 if mode == "bf16" else SVC_F32
+        self.backend = BACKEND_SIMT if force_simt else BACKEND_AUTO
+        self.precise = 1 if mode == "fp32" else 0
+        self.launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _chk(*ts):
+        for t in ts:
+            if t is not None and not t.is_cuda:
+                raise _lib.SvcError("seedvc_b200 kernels need CUDA tensors (no CPU fallback)")
+
+    def _code(self, dt):
+        if dt == torch.bfloat16:
+            return SVC_BF16
+        if dt == torch.float32:
+            return SVC_F32
+        raise TypeError(f"unsupported dtype {dt}")
+
+    def empty(self, *shape, dtype=None, device="cuda"):
+        return torch.empty(*shape, dtype=dtype or self.op_dtype, device=device)
+
+    def zeros(self, *shape, dtype=None, device="cuda"):
+        return torch.zeros(*shape, dtype=dtype or self.op_dtype, device=device)
+
+    # ------------------------------------------------------------------ GEMM
+    def gemm(self, segs, N, *, B, T, bias=None, rowbias=None, act=ACT_NONE, rope=None, gate=None,
+             res=None, alpha=1.0, accumulate=False, out_f32=None, out_op=None, f32=False):
+        """out[b,t,:] = epilogue(sum_s A_s[b, t+shift_s, :] @ W_s.T); see svc_gemm.
+
+        segs: [(A (B, rows, K), shift, W (N, K))]; rope: (table, rope_cols, pos0, q_cols, q_scale).
+        ``f32=True`` forces fp32 operands whatever the mode (small conditioning GEMMs).
+        """
+        d = GemmDesc()
+        dt = torch.float32 if f32 else self.op_dtype
+        d.dtype = SVC_F32 if f32 else self.op_code
+        d.B, d.T, d.N, d.n_seg = B, T, N, len(segs)
+        for i, (A, shift, W) in enumerate(segs):
+            self._chk(A, W)
+            assert A.dtype == dt and W.dtype == dt, (A.dtype, W.dtype, dt)
+            assert A.dim() == 3 and A.stride(2) == 1 and W.dim() == 2 and W.stride(1) == 1
+            assert A.shape[0] == B and W.shape[0] == N and W.shape[1] == A.shape[2]
+            d.a_ptr[i] = A.data_ptr()
+            d.a_bstride[i], d.a_rstride[i] = A.stride(0), A.stride(1)
+            d.a_rows[i], d.a_shift[i] = A.shape[1], shift
+            d.w_ptr[i], d.w_rstride[i], d.K[i] = W.data_ptr(), W.stride(0), W.shape[1]
+        pair = act in (_lib.ACT_SWIGLU_PAIR, _lib.ACT_TANH_SIG_PAIR)
+        n_out = N // 2 if pair else N
+        self._chk(bias, rowbias, gate, res, out_f32, out_op)
+        if bias is not None:
+            assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+            d.bias = bias.data_ptr()
+        if rowbias is not None:
+            assert rowbias.dtype == torch.float32 and rowbias.shape == (B, N) and rowbias.stride(1) == 1
+            d.rowbias, d.rowbias_bstride = rowbias.data_ptr(), rowbias.stride(0)
+        d.act = act
+        if rope is not None:
+            tab, rope_cols, pos0, q_cols, q_scale = rope
+            assert act == ACT_ROPE and tab.dtype == torch.float32 and tab.is_contiguous()
+            assert tab.shape[0] >= pos0 + T and tab.shape[1:] == (32, 2)
+            d.rope_tab, d.rope_cols, d.rope_pos0 = tab.data_ptr(), rope_cols, pos0
+            d.q_cols, d.q_scale = q_cols, q_scale
+        if gate is not None:
+            assert gate.dtype == torch.float32 and gate.shape == (B, n_out) and gate.stride(1) == 1
+            d.gate, d.gate_bstride = gate.data_ptr(), gate.stride(0)
+        if res is not None:
+            assert res.dtype == torch.float32 and res.shape == (B, T, n_out) and res.stride(2) == 1
+            d.res, d.res_bstride, d.res_rstride = res.data_ptr(), res.stride(0), res.stride(1)
+        d.alpha, d.accumulate = float(alpha), int(bool(accumulate))
+        if out_f32 is not None:
+            assert out_f32.dtype == torch.float32 and out_f32.shape == (B, T, n_out)
+            assert out_f32.stride(2) == 1
+            d.out_f32 = out_f32.data_ptr()
+            d.of_bstride, d.of_rstride = out_f32.stride(0), out_f32.stride(1)
+        if out_op is not None:
+            assert out_op.dtype == dt and out_op.shape == (B, T, n_out) and out_op.stride(2) == 1
+            d.out_op = out_op.data_ptr()
+            d.oo_bstride, d.oo_rstride = out_op.stride(0), out_op.stride(1)
+        self.launches += 1
+        check(self.lib.svc_gemm(C.byref(d), self.backend, self._stream()), "svc_gemm")
+
+    # ------------------------------------------------------------------ attention
+    def attention(self, qkv, out, H, kv_len):
+        """qkv: (B, T, 3*H*64) packed [q|k|v] (RoPE + scale applied); out: (B, T, H*64)."""
+        self._chk(qkv, out, kv_len)
+        B, T, W = qkv.shape
+        D = H * 64
+        assert W == 3 * D and qkv.stride(2) == 1 and out.shape == (B, T, D) and out.stride(2) == 1
+        assert qkv.dtype == out.dtype and kv_len.dtype == torch.int32 and kv_len.numel() == B
+        es = qkv.element_size()
+        base = qkv.data_ptr()
+        self.launches += 1
+        check(self.lib.svc_attention(base, base + D * es, base + 2 * D * es, qkv.stride(0),
+                                     qkv.stride(1), out.data_ptr(), out.stride(0), out.stride(1),
+                                     B, T, H, kv_len.data_ptr(), self._code(qkv.dtype), self.backend,
+                                     self._stream()), "svc_attention")
+
+    # ------------------------------------------------------------------ norms
+    def norm_mod(self, x, out, *, gamma=None, mul=None, add=None, eps=1e-5, mode=0):
+        """out = norm(x) * gamma * mul + add; mode 0 RMSNorm, 1 LayerNorm(no affine)."""
+        self._chk(x, out, gamma, mul, add)
+        B, T, D = x.shape
+        assert x.dtype == torch.float32 and x.stride(2) == 1 and out.shape == x.shape
+        assert out.stride(2) == 1
+        for v in (gamma, mul, add):
+            assert v is None or (v.dtype == torch.float32 and v.numel() == D and v.is_contiguous())
+        self.launches += 1
+        check(self.lib.svc_norm_mod(x.data_ptr(), x.stride(0), x.stride(1), _ptr(gamma), _ptr(mul),
+                                    _ptr(add), float(eps), mode, out.data_ptr(), out.stride(0),
+                                    out.stride(1), B, T, D, self._code(out.dtype), self._stream()),
+              "svc_norm_mod")
+
+    # ------------------------------------------------------------------ BigVGAN activations
+    def snake(self, x, out, a, inv_b):
+        """Anti-aliased SnakeBeta on contiguous (B, L, C)."""
+        self._chk(x, out, a, inv_b)
+        B, L, Cc = x.shape
+        assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape
+        assert a.dtype == torch.float32 and a.numel() == Cc and inv_b.numel() == Cc
+        self.launches += 1
+        check(self.lib.svc_snake_aa(x.data_ptr(), self._code(x.dtype), out.data_ptr(),
+                                    self._code(out.dtype), a.data_ptr(), inv_b.data_ptr(), B, L, Cc,
+                                    self.precise, self._stream()), "svc_snake_aa")
+
+    def snake_conv_post(self, x, a, inv_b, w, bias, out, use_tanh):
+        """x (B, L, C) fp32 -> out (B, L) fp32; w (k, C) fp32."""
+        self._chk(x, a, inv_b, w, bias, out)
+        B, L, Cc = x.shape
+        assert x.dtype == torch.float32 and x.is_contiguous() and out.shape == (B, L)
+        assert out.is_contiguous() and w.is_contiguous() and w.shape[1] == Cc
+        self.launches += 1
+        check(self.lib.svc_snake_conv_post(x.data_ptr(), a.data_ptr(), inv_b.data_ptr(), w.data_ptr(),
+                                           _ptr(bias), out.data_ptr(), B, L, Cc, w.shape[0],
+                                           int(bool(use_tanh)), self.precise, self._stream()),
+              "svc_snake_conv_post")
+
+    # ------------------------------------------------------------------ sampler
+    def cfg_euler(self, x, v, coefs, dt, prompt_len, x_lens=None, x_op=None):
+        """x += dt * sum_i coefs[i] * v[i*B:(i+1)*B]; zero prompt / padded rows."""
+        self._chk(x, v, x_lens, x_op)
+        B, T, Cc = x.shape
+        nb = len(coefs)
+        assert x.dtype == torch.float32 and x.is_contiguous() and v.is_contiguous()
+        assert v.shape == (nb * B, T, Cc) and v.dtype == torch.float32
+        c = list(coefs) + [0.0] * (3 - nb)
+        if x_op is not None:
+            assert x_op.is_contiguous() and x_op.shape == x.shape
+        self.launches += 1
+        check(self.lib.svc_cfg_euler(x.data_ptr(), v.data_ptr(), nb, c[0], c[1], c[2], float(dt), B, T,
+                                     Cc, int(prompt_len), _ptr(x_lens), _ptr(x_op),
+                                     self._code(x_op.dtype) if x_op is not None else self.op_code,
+                                     self._stream()), "svc_cfg_euler")
+
+    def bct_to_btc(self, inp, out, zero_from=0, zero_to=0):
+        """(B, C, T) fp32 contiguous -> (B, T, C) view `out` (any float dtype)."""
+        self._chk(inp, out)
+        B, Cc, T = inp.shape
+        assert inp.dtype == torch.float32 and inp.is_contiguous()
+        assert out.shape == (B, T, Cc) and out.stride(2) == 1
+        self.launches += 1
+        check(self.lib.svc_bct_to_btc(inp.data_ptr(), out.data_ptr(), out.stride(0), out.stride(1), B,
+                                      Cc, T, zero_from, zero_to, self._code(out.dtype),
+                                      self._stream()), "svc_bct_to_btc")
+
+    def btc_to_bct(self, inp, out):
+        self._chk(inp, out)
+        B, T, Cc = inp.shape
+        assert inp.dtype == torch.float32 and inp.is_contiguous() and out.is_contiguous()
+        assert out.shape == (B, Cc, T) and out.dtype == torch.float32
+        self.launches += 1
+        check(self.lib.svc_btc_to_bct(inp.data_ptr(), out.data_ptr(), B, T, Cc, self._stream()),
+              "svc_btc_to_bct")
+
+    def cast(self, inp, out):
+        self._chk(inp, out)
+        assert inp.dtype == torch.float32 and inp.is_contiguous() and out.is_contiguous()
+        assert inp.numel() == out.numel()
+        self.launches += 1
+        check(self.lib.svc_cast(inp.data_ptr(), out.data_ptr(), inp.numel(), self._code(out.dtype),
+                                self._stream()), "svc_cast")
+
+    def reflect_halo(self, buf, T, pad, lens=None):
+        """buf: (B, T + 2*pad, C) with the body at rows [pad, pad+T)."""
+        self._chk(buf, lens)
+        B, R, Cc = buf.shape
+        assert R == T + 2 * pad and buf.stride(2) == 1
+        self.launches += 1
+        check(self.lib.svc_reflect_halo(buf.data_ptr(), buf.stride(0), buf.stride(1), B, T, Cc, pad,
+                                        _ptr(lens), self._code(buf.dtype), self._stream()),
+              "svc_reflect_halo")
+
+    def timestep_embedding(self, t, freqs, out):
+        self._chk(t, freqs, out)
+        n, half = t.numel(), freqs.numel()
+        assert out.shape == (n, 2 * half) and out.is_contiguous() and out.dtype == torch.float32
+        assert t.dtype == torch.float32 and freqs.dtype == torch.float32
+        self.launches += 1
+        check(self.lib.svc_timestep_embedding(t.data_ptr(), freqs.data_ptr(), out.data_ptr(), n, half,
+                                              self._stream()), "svc_timestep_embedding")
+
+    def set_rows(self, src, dst):
+        """dst[b, :] = src[b or 0, :]; dst is a (B, D) strided view, src (B, D) or (1, D)."""
+        self._chk(src, dst)
+        B, D = dst.shape
+        assert src.dtype == torch.float32 and dst.dtype == torch.float32
+        assert src.stride(1) == 1 and dst.stride(1) == 1 and src.shape[1] == D
+        sb = 0 if src.shape[0] == 1 else src.stride(0)
+        self.launches += 1
+        check(self.lib.svc_set_rows(src.data_ptr(), sb, dst.data_ptr(), dst.stride(0), B, D,
+                                    self._stream()), "svc_set_rows")

@@ -1,0 +1,113 @@
+"""Host orchestration (weight folding, hoisting, CFG layouts, polyphase upsampling ...) checked on
+CPU against the reference's golden outputs, with tests/emu_ops.py standing in for the CUDA
+library.  The kernels themselves are checked on the GPU (tests/test_gpu_*.py)."""
+import pytest
+import torch
+
+import seedvc_b200  # noqa: F401
+from seedvc_b200 import configs, synth
+from seedvc_b200.bigvgan import BigVGAN
+from seedvc_b200.dit_engine import DiTEngine
+from seedvc_b200.flow_matching import CFM
+from seedvc_b200.flow_matching_v2 import CFM as CFMv2, DiT as DiTv2
+from conftest import load_golden, rel_l2
+from emu_ops import EmuOps
+
+V1 = ["v1_small_scaled_cfg", "v1_small_scaled_nocfg", "v1_tiny_scaled_cfg", "v1_base_scaled_cfg",
+      "v1_tiny_full"]
+V2 = ["v2_small_3branch", "v2_small_spk_only", "v2_small_txt_only", "v2_small_nocfg",
+      "v2_small_random_voice"]
+
+
+def emu_engine(estimator):
+    eng = DiTEngine(estimator.spec, EmuOps())
+    eng.load_weights(estimator.state_dict(), "cpu")
+    estimator.engine = lambda: eng
+    return eng
+
+
+def v1_case(name):
+    g = load_golden(name)
+    m = g["meta"]
+    args = configs.v1_model_params(m["model"])
+    if m["scaled"]:
+        args = configs.scaled_down(args)
+    cfm = CFM(args)
+    emu_engine(cfm.estimator)
+    cfm.estimator.setup_caches(1, 8192)
+    mu, prompt, style, z = synth.synth_batch(1, m["T"], m["Tp"], args.DiT.in_channels,
+                                             args.DiT.content_dim)
+    return g, m, cfm, (mu, prompt, style, z)
+
+
+@pytest.mark.parametrize("name", V1)
+def test_v1_host_logic(name):
+    g, m, cfm, (mu, prompt, style, z) = v1_case(name)
+    T, Tp = m["T"], m["Tp"]
+    t_span = torch.linspace(0, 1, m["n_steps"] + 1)
+    x0 = z.clone()
+    px = torch.zeros_like(x0)
+    px[..., :Tp] = prompt
+    x0[..., :Tp] = 0
+    v0 = cfm.estimator(x0, px, torch.tensor([T]), t_span[0:1], style, mu)
+    assert rel_l2(v0, g["v0"]) < 1e-4
+    out = cfm.solve_euler(z.clone(), torch.tensor([T]), prompt, mu, style, None, t_span, m["cfg"])
+    assert rel_l2(out, g["out"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", V2)
+def test_v2_host_logic(name):
+    g = load_golden(name)
+    m = g["meta"]
+    kw = configs.v2_estimator_kwargs()
+    cfm = CFMv2(DiTv2(**kw))
+    emu_engine(cfm.estimator)
+    mu, prompt, style, z = synth.synth_batch(1, m["T"], m["Tp"], kw["in_channels"], kw["content_dim"])
+    t_span = torch.linspace(0, 1, m["n_steps"] + 1)
+    t_span = t_span + (-1) * (torch.cos(torch.pi / 2 * t_span) - 1 + t_span)
+    out = cfm.solve_euler(z.clone(), torch.tensor([m["T"]]), prompt, mu, style, t_span, m["cfg"],
+                          m["random_voice"])
+    assert rel_l2(out, g["out"]) < 1e-4
+
+
+def test_batched_equals_per_utterance():
+    """Batch of 2 with different lengths == two batch-1 runs (SURVEY App. D-1 semantics)."""
+    args = configs.scaled_down(configs.v1_model_params("whisper_small"))
+    cfm = CFM(args)
+    emu_engine(cfm.estimator)
+    T, Tp = 40, 9
+    mu, prompt, style, z = synth.synth_batch(2, T, Tp, 80, args.DiT.content_dim)
+    lens = torch.tensor([T, 29])
+    t_span = torch.linspace(0, 1, 3)
+    out = cfm.solve_euler(z.clone(), lens, prompt, mu, style, None, t_span, 0.7)
+    for b in range(2):
+        n = int(lens[b])
+        one = cfm.solve_euler(z[b:b + 1, :, :n].clone(), lens[b:b + 1], prompt[b:b + 1],
+                              mu[b:b + 1, :n], style[b:b + 1], None, t_span, 0.7)
+        assert rel_l2(out[b:b + 1, :, :n], one) < 1e-5
+        assert float(out[b, :, n:].abs().max()) == 0.0 if n < T else True
+
+
+@pytest.mark.parametrize("name", ["bigvgan_22k_t12", "bigvgan_22k_b2_t7"])
+def test_bigvgan_host_logic(name):
+    g = load_golden(name)
+    m = g["meta"]
+    h = configs.bigvgan_h(m["config"])
+    voc = BigVGAN(h)
+    w = voc._build_weights(EmuOps())
+    voc._prepare = lambda: w
+    mel = synth.synth_mel(m["B"], h.num_mels, m["Tm"])
+    wav = voc(mel)
+    assert wav.shape == g["wav"].shape
+    assert rel_l2(wav, g["wav"]) < 1e-4
+
+
+def test_bigvgan_loads_weight_norm_checkpoint():
+    h = configs.bigvgan_h()
+    voc = BigVGAN(h)
+    sd = voc.state_dict()
+    v = sd.pop("conv_pre.weight").clone()
+    g = v.flatten(1).norm(dim=1).view(-1, 1, 1) * 1.5
+    sd["conv_pre.weight_v"], sd["conv_pre.weight_g"] = v * 3.0, g
+    voc.load_state_dict(sd)
+    assert torch.allclose(voc.conv_pre.weight, v * 1.5, atol=1e-6)
