@@ -1,0 +1,173 @@
+"""End-to-end parity on the B200 through the package's public API (which calls the C ABI):
+
+* every golden fixture (outputs of the REAL reference, tests/golden/) in fp32 mode
+  (rel-L2 <= 1e-3, north_star) and bf16 mode (rel-L2 <= 1e-2), per estimator call (v0) and
+  after the whole Euler solve;
+* the oracle on seeded inputs at sizes it finishes in seconds;
+* size-independent properties at BASELINE config-2 frame counts (T = 2580): batch invariance,
+  zeroed prompt region, determinism.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import seedvc_b200  # noqa: E402,F401
+from seedvc_b200 import configs, synth  # noqa: E402
+from seedvc_b200.bigvgan import BigVGAN  # noqa: E402
+from seedvc_b200.flow_matching import CFM  # noqa: E402
+from seedvc_b200.flow_matching_v2 import CFM as CFMv2, DiT as DiTv2  # noqa: E402
+from conftest import load_golden, rel_l2  # noqa: E402
+
+DEV = "cuda"
+TOL = {"fp32": 1e-3, "bf16": 1e-2}
+V1 = ["v1_small_scaled_cfg", "v1_small_scaled_nocfg", "v1_tiny_scaled_cfg", "v1_base_scaled_cfg",
+      "v1_tiny_full", "v1_small_full", "v1_base_full"]
+V2 = ["v2_small_3branch", "v2_small_spk_only", "v2_small_txt_only", "v2_small_nocfg",
+      "v2_small_random_voice"]
+
+_models = {}
+
+
+def v1_model(model, scaled, mode):
+    key = (model, scaled)
+    if key not in _models:
+        args = configs.v1_model_params(model)
+        if scaled:
+            args = configs.scaled_down(args)
+        cfm = CFM(args).to(DEV)
+        cfm.estimator.setup_caches(1, 8192)
+        _models[key] = (cfm, args)
+    cfm, args = _models[key]
+    cfm.set_mode(mode)
+    return cfm, args
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", V1)
+def test_v1_golden(name, mode):
+    g = load_golden(name)
+    m = g["meta"]
+    cfm, args = v1_model(m["model"], m["scaled"], mode)
+    T, Tp = m["T"], m["Tp"]
+    mu, prompt, style, z = [t.to(DEV) for t in
+                            synth.synth_batch(1, T, Tp, args.DiT.in_channels, args.DiT.content_dim)]
+    t_span = torch.linspace(0, 1, m["n_steps"] + 1, device=DEV)
+    x0 = z.clone()
+    px = torch.zeros_like(x0)
+    px[..., :Tp] = prompt
+    x0[..., :Tp] = 0
+    xl = torch.tensor([T], device=DEV)
+    v0 = cfm.estimator(x0, px, xl, t_span[0:1], style, mu)
+    e_v = rel_l2(v0.cpu(), g["v0"])
+    out = cfm.solve_euler(z.clone(), xl, prompt, mu, style, None, t_span, m["cfg"])
+    e_o = rel_l2(out.cpu(), g["out"])
+    print(f"{name} [{mode}] velocity rel-L2 {e_v:.2e}  end-to-end rel-L2 {e_o:.2e}")
+    assert e_v < TOL[mode] and e_o < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", V2)
+def test_v2_golden(name, mode):
+    g = load_golden(name)
+    m = g["meta"]
+    if "v2" not in _models:
+        _models["v2"] = CFMv2(DiTv2(**configs.v2_estimator_kwargs())).to(DEV)
+    cfm = _models["v2"]
+    cfm.set_mode(mode)
+    kw = configs.v2_estimator_kwargs()
+    mu, prompt, style, z = [t.to(DEV) for t in
+                            synth.synth_batch(1, m["T"], m["Tp"], kw["in_channels"], kw["content_dim"])]
+    t_span = torch.linspace(0, 1, m["n_steps"] + 1, device=DEV)
+    t_span = t_span + (-1) * (torch.cos(torch.pi / 2 * t_span) - 1 + t_span)
+    out = cfm.solve_euler(z.clone(), torch.tensor([m["T"]], device=DEV), prompt, mu, style, t_span,
+                          m["cfg"], m["random_voice"])
+    e = rel_l2(out.cpu(), g["out"])
+    print(f"{name} [{mode}] end-to-end rel-L2 {e:.2e}")
+    assert e < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["bigvgan_22k_t12", "bigvgan_22k_b2_t7"])
+def test_bigvgan_golden(name, mode):
+    g = load_golden(name)
+    m = g["meta"]
+    if "voc" not in _models:
+        _models["voc"] = BigVGAN(configs.bigvgan_h(m["config"])).to(DEV)
+    voc = _models["voc"]
+    voc.set_mode(mode)
+    mel = synth.synth_mel(m["B"], voc.h.num_mels, m["Tm"]).to(DEV)
+    wav = voc(mel)
+    assert wav.shape == g["wav"].shape
+    e = rel_l2(wav.cpu(), g["wav"])
+    print(f"{name} [{mode}] waveform rel-L2 {e:.2e}")
+    assert e < TOL[mode]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_v1_against_oracle_ragged_batch(mode, manifest):
+    """Seeded batch of 3 utterances of different lengths vs the oracle's per-utterance runs."""
+    import seedvc_oracle as orc
+
+    cfm, args = v1_model("whisper_small", True, mode)
+    sd = synth.synth_state_dict(manifest["keys_whisper_small_scaled"])
+    T, Tp = 300, 41
+    mu, prompt, style, z = synth.synth_batch(3, T, Tp, 80, args.DiT.content_dim, first_id=50)
+    lens = torch.tensor([300, 257, 129])
+    t_span = torch.linspace(0, 1, 4)
+    want = orc.solve_euler_v1(sd, args, z, lens, prompt, mu, style, t_span, 0.7)
+    out = cfm.solve_euler(z.to(DEV), lens.to(DEV), prompt.to(DEV), mu.to(DEV), style.to(DEV), None,
+                          t_span.to(DEV), 0.7).cpu()
+    for b in range(3):
+        n = int(lens[b])
+        e = rel_l2(out[b, :, :n], want[b, :, :n])
+        print(f"ragged[{b}] len {n} [{mode}] rel-L2 {e:.2e}")
+        assert e < TOL[mode]
+        assert float(out[b, :, n:].abs().max() if n < T else 0.0) == 0.0
+        assert float(out[b, :, :Tp].abs().max()) == 0.0
+
+
+def test_bigvgan_against_oracle_longer(manifest):
+    import seedvc_oracle as orc
+
+    if "voc" not in _models:
+        _models["voc"] = BigVGAN(configs.bigvgan_h()).to(DEV)
+    voc = _models["voc"]
+    sd = synth.synth_state_dict(manifest["keys_bigvgan_22k"])
+    mel = synth.synth_mel(1, 80, 65, seed=11)       # one streaming block (config 5: 65 frames)
+    want = orc.bigvgan_forward(sd, voc.h, mel)
+    for mode in ("fp32", "bf16"):
+        voc.set_mode(mode)
+        wav = voc(mel.to(DEV)).cpu()
+        e = rel_l2(wav, want)
+        print(f"bigvgan 65 frames [{mode}] rel-L2 {e:.2e}")
+        assert e < TOL[mode]
+
+
+def test_full_length_properties():
+    """T = 2580 (30 s context, BASELINE config 2): utterance results do not depend on what else is
+    in the batch, the prompt region stays zero, and two runs are bit-identical."""
+    cfm, args = v1_model("whisper_small", False, "bf16")
+    T, Tp, B = 2580, 430, 3
+    mu, prompt, style, z = [t.to(DEV) for t in synth.synth_batch(B, T, Tp, 80, 512, first_id=7)]
+    lens = torch.full((B,), T, device=DEV)
+    t_span = torch.linspace(0, 1, 3, device=DEV)
+    out = cfm.solve_euler(z.clone(), lens, prompt, mu, style, None, t_span, 0.7)
+    out2 = cfm.solve_euler(z.clone(), lens, prompt, mu, style, None, t_span, 0.7)
+    assert torch.equal(out, out2)
+    assert torch.isfinite(out).all()
+    assert float(out[:, :, :Tp].abs().max()) == 0.0
+    one = cfm.solve_euler(z[1:2].clone(), lens[1:2], prompt[1:2], mu[1:2], style[1:2], None, t_span, 0.7)
+    assert rel_l2(out[1:2].cpu(), one.cpu()) < 1e-6
+
+
+def test_inference_api_and_cpu_refusal():
+    cfm, args = v1_model("xlsr_tiny", True, "bf16")
+    mu, prompt, style, _ = [t.to(DEV) for t in synth.synth_batch(2, 60, 20, 80, args.DiT.content_dim)]
+    torch.manual_seed(3)
+    out = cfm.inference(mu, torch.tensor([60, 60], device=DEV), prompt, style, None, 4,
+                        inference_cfg_rate=0.7)
+    assert out.shape == (2, 80, 60) and torch.isfinite(out).all()
+    cpu = CFM(configs.scaled_down(configs.v1_model_params("xlsr_tiny")))
+    with pytest.raises(RuntimeError):
+        cpu.inference(mu.cpu(), torch.tensor([60, 60]), prompt.cpu(), style.cpu(), None, 2)

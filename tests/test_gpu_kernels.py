@@ -1,0 +1,288 @@
+"""Per-kernel parity on the B200: every C-ABI entry point against a plain fp32 PyTorch
+restatement of the same op (tests/emu_ops.py run on the GPU).  Tolerances are written per test:
+fp32 kernels rel-L2 <= 1e-5; bf16 tensor-core kernels are compared on bf16-rounded inputs so only
+accumulation order / output rounding differ (rel-L2 <= 4e-3 for bf16 outputs, 1e-4 for fp32 outputs).
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import seedvc_b200  # noqa: E402,F401
+from seedvc_b200 import _lib  # noqa: E402
+from seedvc_b200.ops import Ops  # noqa: E402
+from conftest import rel_l2  # noqa: E402
+from emu_ops import EmuOps  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (scale * torch.randn(*shape, generator=g)).to(DEV).to(dtype)
+
+
+def ops_for(mode, simt=False):
+    return Ops(mode, force_simt=simt)
+
+
+def run_gemm_case(mode, simt, B, T, N, Ks, shifts=None, rows=None, bias=False, rowbias=False,
+                  act=0, gate=False, res=False, alpha=1.0, accumulate=False, both_out=False,
+                  rope=False, seed=0):
+    ops, emu = ops_for(mode, simt), EmuOps()
+    od = ops.op_dtype
+    shifts = shifts or [0] * len(Ks)
+    rows = rows or T
+    segs, segs_ref = [], []
+    for i, K in enumerate(Ks):
+        A = rnd(B, rows, K, seed=seed + 10 * i, dtype=od)
+        W = rnd(N, K, seed=seed + 10 * i + 1, scale=1 / math.sqrt(K * len(Ks)), dtype=od)
+        segs.append((A, shifts[i], W))
+        segs_ref.append((A.float(), shifts[i], W.float()))
+    pair = act in (2, 3)
+    n_out = N // 2 if pair else N
+    kw = {}
+    if bias:
+        kw["bias"] = rnd(N, seed=seed + 100)
+    if rowbias:
+        kw["rowbias"] = rnd(B, N, seed=seed + 101)
+    if gate:
+        kw["gate"] = rnd(B, n_out, seed=seed + 102)
+    if res:
+        kw["res"] = rnd(B, T, n_out, seed=seed + 103)
+    if rope:
+        from seedvc_b200.dit_engine import rope_table
+        kw["rope"] = (rope_table(T + 3).to(DEV), 2 * (N // 3), 2, N // 3, 0.125)
+        act = 4
+    init = rnd(B, T, n_out, seed=seed + 104)
+    out_f32 = init.clone()
+    out_ref = init.clone()
+    out_op = torch.zeros(B, T, n_out, dtype=od, device=DEV) if both_out else None
+    out_op_ref = torch.zeros(B, T, n_out, device=DEV) if both_out else None
+    ops.gemm(segs, N, B=B, T=T, act=act, alpha=alpha, accumulate=accumulate, out_f32=out_f32,
+             out_op=out_op, **kw)
+    emu.gemm(segs_ref, N, B=B, T=T, act=act, alpha=alpha, accumulate=accumulate, out_f32=out_ref,
+             out_op=out_op_ref, **kw)
+    torch.cuda.synchronize()
+    tol = 1e-5 if mode == "fp32" else 2e-4
+    e = rel_l2(out_f32, out_ref)
+    assert e < tol, f"out_f32 rel-L2 {e}"
+    if both_out:
+        e2 = rel_l2(out_op.float(), out_ref)
+        assert e2 < (1e-5 if mode == "fp32" else 4e-3), f"out_op rel-L2 {e2}"
+
+
+GEMM_SHAPES = [
+    # B, T, N, Ks
+    (1, 128, 128, [64]),
+    (1, 128, 128, [128]),
+    (2, 200, 512, [512]),
+    (3, 323, 1536, [512]),
+    (1, 1291, 384, [384]),
+    (2, 77, 24, [24]),
+    (2, 300, 48, [48]),
+    (1, 257, 96, [96]),
+    (2, 130, 80, [512]),
+    (2, 130, 512, [80]),
+    (1, 100, 1152, [384]),
+]
+
+
+@pytest.mark.parametrize("shape", GEMM_SHAPES)
+@pytest.mark.parametrize("mode,simt", [("bf16", False), ("bf16", True), ("fp32", False)])
+def test_gemm_plain(shape, mode, simt):
+    B, T, N, Ks = shape
+    run_gemm_case(mode, simt, B, T, N, Ks)
+
+
+@pytest.mark.parametrize("mode,simt", [("bf16", False), ("fp32", False)])
+def test_gemm_epilogues(mode, simt):
+    run_gemm_case(mode, simt, 2, 150, 256, [128], bias=True, rowbias=True, res=True, alpha=0.5,
+                  both_out=True)
+    run_gemm_case(mode, simt, 2, 150, 256, [128], bias=True, act=1, both_out=True)          # silu
+    run_gemm_case(mode, simt, 2, 150, 512, [128], act=2, both_out=True)                      # swiglu
+    run_gemm_case(mode, simt, 2, 150, 512, [128], rowbias=True, act=3, both_out=True)        # gate
+    run_gemm_case(mode, simt, 2, 150, 256, [128], gate=True, res=True, both_out=True)        # v2
+    run_gemm_case(mode, simt, 2, 150, 256, [128], bias=True, res=True, alpha=1 / 3,
+                  accumulate=True, both_out=True)
+    run_gemm_case(mode, simt, 2, 150, 384, [128], rope=True, both_out=True)
+
+
+@pytest.mark.parametrize("mode,simt", [("bf16", False), ("fp32", False)])
+def test_gemm_segments(mode, simt):
+    # concat-free linear over two operands
+    run_gemm_case(mode, simt, 2, 140, 128, [128, 128], bias=True)
+    run_gemm_case(mode, simt, 2, 140, 128, [128, 80], bias=True)
+    # k-tap dilated conv with zero padding (shifts outside [0, rows) read zeros)
+    run_gemm_case(mode, simt, 2, 300, 96, [96] * 3, shifts=[-5, 0, 5], bias=True)
+    run_gemm_case(mode, simt, 2, 300, 48, [48] * 7, shifts=[(t - 3) * 3 for t in range(7)])
+    run_gemm_case(mode, simt, 1, 200, 24, [24] * 11, shifts=[t - 5 for t in range(11)], bias=True)
+    # taps over a padded buffer (WaveNet reflect layout): rows = T + 4
+    run_gemm_case(mode, simt, 2, 131, 256, [128] * 5, shifts=[0, 1, 2, 3, 4], rows=135, rowbias=True,
+                  act=3)
+
+
+def test_gemm_conv_taps_share_weight_buffer():
+    """Taps taken as slices of one (k, N, K) tensor (one TMA map, row offsets)."""
+    ops, emu = ops_for("bf16"), EmuOps()
+    B, T, N, K, k = 2, 260, 192, 192, 7
+    A = rnd(B, T, K, dtype=torch.bfloat16)
+    W = rnd(k, N, K, seed=3, scale=1 / math.sqrt(K * k), dtype=torch.bfloat16)
+    out = torch.empty(B, T, N, device=DEV)
+    ref = torch.empty(B, T, N, device=DEV)
+    ops.gemm([(A, (t - 3) * 5, W[t]) for t in range(k)], N, B=B, T=T, out_f32=out)
+    emu.gemm([(A.float(), (t - 3) * 5, W[t].float()) for t in range(k)], N, B=B, T=T, out_f32=ref)
+    assert rel_l2(out, ref) < 2e-4
+
+
+@pytest.mark.parametrize("mode,simt", [("bf16", False), ("bf16", True), ("fp32", False)])
+@pytest.mark.parametrize("B,T,H,lens", [(1, 65, 2, None), (2, 128, 2, [128, 100]),
+                                        (2, 323, 6, [323, 17]), (1, 1291, 8, None),
+                                        (3, 257, 2, [257, 256, 129])])
+def test_attention(mode, simt, B, T, H, lens):
+    ops, emu = ops_for(mode, simt), EmuOps()
+    od = ops.op_dtype
+    D = H * 64
+    qkv = rnd(B, T, 3 * D, seed=T, dtype=od)
+    qkv[..., :D] *= 0.125
+    kv = torch.tensor(lens or [T] * B, dtype=torch.int32, device=DEV)
+    out = torch.zeros(B, T, D, dtype=od, device=DEV)
+    ref = torch.zeros(B, T, D, device=DEV)
+    ops.attention(qkv, out, H, kv)
+    emu.attention(qkv.float(), ref, H, kv)
+    torch.cuda.synchronize()
+    e = rel_l2(out.float(), ref)
+    assert e < (1e-5 if mode == "fp32" else 6e-3), f"rel-L2 {e}"
+
+
+@pytest.mark.parametrize("D", [128, 384, 512, 768])
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_norm_mod(D, mode):
+    ops, emu = ops_for(mode), EmuOps()
+    B, T = 2, 77
+    x = rnd(B, T + 2, D, seed=D)[:, 2:, :]          # strided rows (token offset view)
+    g, m, a = rnd(D, seed=1), rnd(D, seed=2), rnd(D, seed=3)
+    for kw in (dict(gamma=g), dict(gamma=g, mul=m, add=a), dict(mul=m, add=a, eps=1e-6, mode=1)):
+        out = torch.zeros(B, T, D, dtype=ops.op_dtype, device=DEV)
+        ref = torch.zeros(B, T, D, device=DEV)
+        ops.norm_mod(x, out, **kw)
+        emu.norm_mod(x, ref, **kw)
+        e = rel_l2(out.float(), ref)
+        assert e < (1e-5 if mode == "fp32" else 4e-3)
+
+
+@pytest.mark.parametrize("C,L", [(24, 1000), (48, 515), (96, 300), (768, 70), (192, 129), (16, 40),
+                                 (32, 12), (8, 5)])
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_snake(C, L, mode):
+    ops, emu = ops_for(mode), EmuOps()
+    B = 2
+    x = rnd(B, L, C, seed=C + L, scale=2.0)
+    a = torch.exp(0.3 * rnd(C, seed=1))
+    inv_b = 1.0 / (torch.exp(0.3 * rnd(C, seed=2)) + 1e-9)
+    out = torch.zeros(B, L, C, dtype=ops.op_dtype, device=DEV)
+    ref = torch.zeros(B, L, C, device=DEV)
+    ops.snake(x, out, a, inv_b)
+    emu.snake(x, ref, a, inv_b)
+    e = rel_l2(out.float(), ref)
+    assert e < (1e-5 if mode == "fp32" else 4e-3), f"rel-L2 {e}"
+    if mode == "bf16":   # bf16 input variant
+        xb = x.to(torch.bfloat16)
+        ops.snake(xb, out, a, inv_b)
+        emu.snake(xb.float(), ref, a, inv_b)
+        assert rel_l2(out.float(), ref) < 4e-3
+
+
+def test_snake_known_answer():
+    """SURVEY section 8c KAT: SnakeBeta(4, logscale, alpha=beta=0) on arange(40)/10."""
+    ops = ops_for("fp32")
+    x = (torch.arange(40, dtype=torch.float32).reshape(1, 4, 10) / 10).transpose(1, 2).contiguous().to(DEV)
+    out = torch.zeros(1, 10, 4, device=DEV)
+    one = torch.ones(4, device=DEV)
+    ops.snake(x, out, one, 1.0 / (one + 1e-9))
+    row0 = out[0, :, 0].cpu()
+    want = torch.tensor([0.0032857, 0.1064557, 0.2406803, 0.3870877, 0.5515801, 0.7297742, 0.9190356,
+                         1.1126915, 1.3211195, 1.5065919])
+    assert torch.allclose(row0, want, atol=2e-6)
+
+
+@pytest.mark.parametrize("use_tanh", [False, True])
+def test_snake_conv_post(use_tanh):
+    ops, emu = ops_for("fp32"), EmuOps()
+    B, L, C = 2, 700, 24
+    x = rnd(B, L, C, seed=9)
+    a = torch.exp(0.3 * rnd(C, seed=1))
+    inv_b = 1.0 / (torch.exp(0.3 * rnd(C, seed=2)) + 1e-9)
+    w = rnd(7, C, seed=4, scale=0.2)
+    out, ref = torch.zeros(B, L, device=DEV), torch.zeros(B, L, device=DEV)
+    ops.snake_conv_post(x, a, inv_b, w, None, out, use_tanh)
+    emu.snake_conv_post(x, a, inv_b, w, None, ref, use_tanh)
+    assert rel_l2(out, ref) < 1e-5
+    assert float(out.abs().max()) <= 1.0
+
+
+def test_cfg_euler_and_layout():
+    ops, emu = ops_for("bf16"), EmuOps()
+    B, T, C = 3, 101, 80
+    lens = torch.tensor([101, 64, 7], dtype=torch.int32, device=DEV)
+    for nb, coefs in ((1, [1.0]), (2, [1.7, -0.7]), (3, [2.4, -0.7, -0.7])):
+        x = rnd(B, T, C, seed=nb)
+        v = rnd(nb * B, T, C, seed=nb + 5)
+        xr = x.clone()
+        x_op = torch.zeros(B, T, C, dtype=torch.bfloat16, device=DEV)
+        ops.cfg_euler(x, v, coefs, 0.04, 9, lens, x_op)
+        emu.cfg_euler(xr, v, coefs, 0.04, 9, lens, None)
+        assert rel_l2(x, xr) < 1e-6
+        assert torch.equal(x_op, x.to(torch.bfloat16))
+    src = rnd(2, 80, 45, seed=3)
+    out = torch.zeros(2, 45, 80, device=DEV)
+    ops.bct_to_btc(src, out, zero_from=0, zero_to=5)
+    ref = src.transpose(1, 2).clone()
+    ref[:, :5] = 0
+    assert torch.equal(out, ref)
+    back = torch.zeros(2, 80, 45, device=DEV)
+    ops.btc_to_bct(out, back)
+    assert torch.equal(back, ref.transpose(1, 2))
+    buf = torch.zeros(2, 50, 96, device=DEV)          # strided destination view
+    ops.bct_to_btc(src, buf[:, 3:48, :80])
+    assert torch.equal(buf[:, 3:48, :80], src.transpose(1, 2))
+    c = torch.zeros(2 * 80 * 45, dtype=torch.bfloat16, device=DEV)
+    ops.cast(src, c)
+    assert torch.equal(c, src.flatten().to(torch.bfloat16))
+
+
+def test_reflect_halo_timestep_rows():
+    ops, emu = ops_for("bf16"), EmuOps()
+    B, T, C, pad = 3, 40, 64, 2
+    buf = rnd(B, T + 2 * pad, C, seed=1, dtype=torch.bfloat16)
+    ref = buf.clone()
+    lens = torch.tensor([40, 33, 5], dtype=torch.int32, device=DEV)
+    ops.reflect_halo(buf, T, pad, lens)
+    emu.reflect_halo(ref, T, pad, lens)
+    assert torch.equal(buf, ref)
+    t = torch.tensor([0.0, 0.04, 0.5, 0.96], device=DEV)
+    freqs = torch.exp(-math.log(10000) * torch.arange(128, dtype=torch.float32) / 128).to(DEV)
+    out, want = torch.zeros(4, 256, device=DEV), torch.zeros(4, 256, device=DEV)
+    ops.timestep_embedding(t, freqs, out)
+    emu.timestep_embedding(t, freqs, want)
+    assert float((out - want).abs().max()) < 2e-4
+    dst = torch.zeros(5, 7, 64, device=DEV)
+    src = rnd(5, 64, seed=2)
+    ops.set_rows(src, dst[:, 1, :])
+    ops.set_rows(src[:1], dst[:, 0, :])
+    assert torch.equal(dst[:, 1], src) and torch.equal(dst[:, 0], src[:1].expand(5, 64))
+
+
+def test_no_cpu_fallback():
+    ops = ops_for("bf16")
+    with pytest.raises(_lib.SvcError):
+        ops.cast(torch.zeros(8), torch.zeros(8, dtype=torch.bfloat16))
