@@ -99,8 +99,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
                     mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
                     uint8_t* sa = smem + stage * S::STAGE_BYTES;
                     tma_load_3d(sa, &p.amap[sg.a_map], &full_bar[stage], kb * BK, t0 + sg.shift, b);
-                    tma_load_2d(sa + S::A_BYTES, &p.wmap[sg.w_map], &full_bar[stage], kb * BK,
-                                sg.w_row0 + n0);
+                    // weight maps are rank 3 too (K, rows, 1): the TMA instruction rank must
+                    // match the tensor-map rank
+                    tma_load_3d(sa + S::A_BYTES, &p.wmap[sg.w_map], &full_bar[stage], kb * BK,
+                                sg.w_row0 + n0, 0);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
