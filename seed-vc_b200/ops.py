@@ -33,6 +33,36 @@ class Ops:
         self.backend = BACKEND_SIMT if force_simt else BACKEND_AUTO
         self.precise = 1 if mode == "fp32" else 0
         self.launches = 0
+        self.profile = None      # list of [category, flops, bytes, start_event, end_event] when on
+
+    # ------------------------------------------------------------------ optional per-launch timing
+    def start_profile(self):
+        self.profile = []
+
+    def stop_profile(self):
+        """-> {category: dict(launches, ms, flops, bytes)} (synchronises)."""
+        torch.cuda.synchronize()
+        out = {}
+        for cat, fl, by, e0, e1 in self.profile:
+            d = out.setdefault(cat, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += fl
+            d["bytes"] += by
+        self.profile = None
+        return out
+
+    def _t0(self, cat, flops=0.0, nbytes=0.0):
+        self.launches += 1
+        if self.profile is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.profile.append([cat, flops, nbytes, e0, e1])
+
+    def _t1(self):
+        if self.profile is not None:
+            self.profile[-1][4].record()
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
@@ -111,8 +141,12 @@ class Ops:
             assert out_op.dtype == dt and out_op.shape == (B, T, n_out) and out_op.stride(2) == 1
             d.out_op = out_op.data_ptr()
             d.oo_bstride, d.oo_rstride = out_op.stride(0), out_op.stride(1)
-        self.launches += 1
+        ktot = sum(W.shape[1] for _, _, W in segs)
+        cat = "gemm_f32" if (f32 or self.mode == "fp32") else ("gemm_tc" if self.backend == BACKEND_AUTO
+                                                               else "gemm_simt")
+        self._t0(cat, 2.0 * B * T * N * ktot)
         check(self.lib.svc_gemm(C.byref(d), self.backend, self._stream()), "svc_gemm")
+        self._t1()
 
     # ------------------------------------------------------------------ attention
     def attention(self, qkv, out, H, kv_len):
@@ -124,11 +158,12 @@ class Ops:
         assert qkv.dtype == out.dtype and kv_len.dtype == torch.int32 and kv_len.numel() == B
         es = qkv.element_size()
         base = qkv.data_ptr()
-        self.launches += 1
+        self._t0("attention", 4.0 * B * T * T * D)
         check(self.lib.svc_attention(base, base + D * es, base + 2 * D * es, qkv.stride(0),
                                      qkv.stride(1), out.data_ptr(), out.stride(0), out.stride(1),
                                      B, T, H, kv_len.data_ptr(), self._code(qkv.dtype), self.backend,
                                      self._stream()), "svc_attention")
+        self._t1()
 
     # ------------------------------------------------------------------ norms
     def norm_mod(self, x, out, *, gamma=None, mul=None, add=None, eps=1e-5, mode=0):
@@ -139,11 +174,12 @@ class Ops:
         assert out.stride(2) == 1
         for v in (gamma, mul, add):
             assert v is None or (v.dtype == torch.float32 and v.numel() == D and v.is_contiguous())
-        self.launches += 1
+        self._t0("norm_mod", 0.0, float(B) * T * D * (4 + out.element_size()))
         check(self.lib.svc_norm_mod(x.data_ptr(), x.stride(0), x.stride(1), _ptr(gamma), _ptr(mul),
                                     _ptr(add), float(eps), mode, out.data_ptr(), out.stride(0),
                                     out.stride(1), B, T, D, self._code(out.dtype), self._stream()),
               "svc_norm_mod")
+        self._t1()
 
     # ------------------------------------------------------------------ BigVGAN activations
     def snake(self, x, out, a, inv_b):
@@ -152,10 +188,11 @@ class Ops:
         B, L, Cc = x.shape
         assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape
         assert a.dtype == torch.float32 and a.numel() == Cc and inv_b.numel() == Cc
-        self.launches += 1
+        self._t0("snake_aa", 0.0, float(B) * L * Cc * (x.element_size() + out.element_size()))
         check(self.lib.svc_snake_aa(x.data_ptr(), self._code(x.dtype), out.data_ptr(),
                                     self._code(out.dtype), a.data_ptr(), inv_b.data_ptr(), B, L, Cc,
                                     self.precise, self._stream()), "svc_snake_aa")
+        self._t1()
 
     def snake_conv_post(self, x, a, inv_b, w, bias, out, use_tanh):
         """x (B, L, C) fp32 -> out (B, L) fp32; w (k, C) fp32."""
@@ -163,11 +200,12 @@ class Ops:
         B, L, Cc = x.shape
         assert x.dtype == torch.float32 and x.is_contiguous() and out.shape == (B, L)
         assert out.is_contiguous() and w.is_contiguous() and w.shape[1] == Cc
-        self.launches += 1
+        self._t0("snake_conv_post", 0.0, float(B) * L * (Cc + 1) * 4)
         check(self.lib.svc_snake_conv_post(x.data_ptr(), a.data_ptr(), inv_b.data_ptr(), w.data_ptr(),
                                            _ptr(bias), out.data_ptr(), B, L, Cc, w.shape[0],
                                            int(bool(use_tanh)), self.precise, self._stream()),
               "svc_snake_conv_post")
+        self._t1()
 
     # ------------------------------------------------------------------ sampler
     def cfg_euler(self, x, v, coefs, dt, prompt_len, x_lens=None, x_op=None):
@@ -180,11 +218,12 @@ class Ops:
         c = list(coefs) + [0.0] * (3 - nb)
         if x_op is not None:
             assert x_op.is_contiguous() and x_op.shape == x.shape
-        self.launches += 1
+        self._t0("cfg_euler", 0.0, float(B) * T * Cc * 4 * (2 + nb))
         check(self.lib.svc_cfg_euler(x.data_ptr(), v.data_ptr(), nb, c[0], c[1], c[2], float(dt), B, T,
                                      Cc, int(prompt_len), _ptr(x_lens), _ptr(x_op),
                                      self._code(x_op.dtype) if x_op is not None else self.op_code,
                                      self._stream()), "svc_cfg_euler")
+        self._t1()
 
     def bct_to_btc(self, inp, out, zero_from=0, zero_to=0):
         """(B, C, T) fp32 contiguous -> (B, T, C) view `out` (any float dtype)."""
@@ -192,46 +231,51 @@ class Ops:
         B, Cc, T = inp.shape
         assert inp.dtype == torch.float32 and inp.is_contiguous()
         assert out.shape == (B, T, Cc) and out.stride(2) == 1
-        self.launches += 1
+        self._t0("misc")
         check(self.lib.svc_bct_to_btc(inp.data_ptr(), out.data_ptr(), out.stride(0), out.stride(1), B,
                                       Cc, T, zero_from, zero_to, self._code(out.dtype),
                                       self._stream()), "svc_bct_to_btc")
+        self._t1()
 
     def btc_to_bct(self, inp, out):
         self._chk(inp, out)
         B, T, Cc = inp.shape
         assert inp.dtype == torch.float32 and inp.is_contiguous() and out.is_contiguous()
         assert out.shape == (B, Cc, T) and out.dtype == torch.float32
-        self.launches += 1
+        self._t0("misc")
         check(self.lib.svc_btc_to_bct(inp.data_ptr(), out.data_ptr(), B, T, Cc, self._stream()),
               "svc_btc_to_bct")
+        self._t1()
 
     def cast(self, inp, out):
         self._chk(inp, out)
         assert inp.dtype == torch.float32 and inp.is_contiguous() and out.is_contiguous()
         assert inp.numel() == out.numel()
-        self.launches += 1
+        self._t0("misc")
         check(self.lib.svc_cast(inp.data_ptr(), out.data_ptr(), inp.numel(), self._code(out.dtype),
                                 self._stream()), "svc_cast")
+        self._t1()
 
     def reflect_halo(self, buf, T, pad, lens=None):
         """buf: (B, T + 2*pad, C) with the body at rows [pad, pad+T)."""
         self._chk(buf, lens)
         B, R, Cc = buf.shape
         assert R == T + 2 * pad and buf.stride(2) == 1
-        self.launches += 1
+        self._t0("misc")
         check(self.lib.svc_reflect_halo(buf.data_ptr(), buf.stride(0), buf.stride(1), B, T, Cc, pad,
                                         _ptr(lens), self._code(buf.dtype), self._stream()),
               "svc_reflect_halo")
+        self._t1()
 
     def timestep_embedding(self, t, freqs, out):
         self._chk(t, freqs, out)
         n, half = t.numel(), freqs.numel()
         assert out.shape == (n, 2 * half) and out.is_contiguous() and out.dtype == torch.float32
         assert t.dtype == torch.float32 and freqs.dtype == torch.float32
-        self.launches += 1
+        self._t0("misc")
         check(self.lib.svc_timestep_embedding(t.data_ptr(), freqs.data_ptr(), out.data_ptr(), n, half,
                                               self._stream()), "svc_timestep_embedding")
+        self._t1()
 
     def set_rows(self, src, dst):
         """dst[b, :] = src[b or 0, :]; dst is a (B, D) strided view, src (B, D) or (1, D)."""
@@ -240,6 +284,7 @@ class Ops:
         assert src.dtype == torch.float32 and dst.dtype == torch.float32
         assert src.stride(1) == 1 and dst.stride(1) == 1 and src.shape[1] == D
         sb = 0 if src.shape[0] == 1 else src.stride(0)
-        self.launches += 1
+        self._t0("misc")
         check(self.lib.svc_set_rows(src.data_ptr(), sb, dst.data_ptr(), dst.stride(0), B, D,
                                     self._stream()), "svc_set_rows")
+        self._t1()
