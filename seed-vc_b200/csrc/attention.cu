@@ -14,10 +14,12 @@
 
 namespace svc {
 
-constexpr int AT_BM = 128;   // queries per CTA
+constexpr int AT_BM = 128;   // queries per Q tile (one TMEM lane each)
+constexpr int AT_QT = 2;     // Q tiles per CTA (ping-pong between two softmax groups)
 constexpr int AT_BN = 128;   // keys per block
 constexpr int AT_HD = 64;
-constexpr int AT_KST = 2;    // K / V ring depth
+constexpr int AT_KST = 3;    // K / V ring depth
+constexpr int AT_THREADS = 64 + AT_QT * 128;
 
 struct alignas(64) AttnTcParams {
     CUtensorMap qmap, kmap, vmap;  // (H*64, T, B) bf16 views, box {64, 128, 1}
@@ -30,10 +32,10 @@ struct alignas(64) AttnTcParams {
 struct AttnSmem {
     static constexpr int TILE = AT_BM * AT_HD * 2;          // 16 KB
     static constexpr int Q_OFF = 0;
-    static constexpr int K_OFF = Q_OFF + TILE;
+    static constexpr int K_OFF = Q_OFF + AT_QT * TILE;
     static constexpr int V_OFF = K_OFF + AT_KST * TILE;
-    static constexpr int P_OFF = V_OFF + AT_KST * TILE;     // 2 buffers x (2 tiles of 128x64)
-    static constexpr int BAR_OFF = P_OFF + 2 * 2 * TILE;
+    static constexpr int P_OFF = V_OFF + AT_KST * TILE;     // per group: 2 tiles of 128 x 64
+    static constexpr int BAR_OFF = P_OFF + AT_QT * 2 * TILE;
     static constexpr int TOTAL = BAR_OFF + 512 + 1024;
 };
 
@@ -42,7 +44,36 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t addr) {
     return umma_desc_sw128(addr, 1024, 1024);
 }
 
-__global__ void __launch_bounds__(192, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// 32 lanes x 32 columns store (thread i writes row lane_base + i)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16,"
+        " %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+// One CTA = 256 queries (two Q tiles) of one (batch, head).
+//   warp 0    : TMA producer (Q tiles once, K_j / V_j through mbarrier rings, shared by both tiles)
+//   warp 1    : MMA issuer: S_g = Q_g K_j^T (TMEM, 128 cols per group) and O_g += P_g V_j (TMEM,
+//               64 cols per group, accumulated in place), ordered PV0_j, S0_{j+1}, PV1_j, S1_{j+1}
+//               so the tensor pipe works for one group while the other group is in softmax
+//   warps 2-5 / 6-9 : softmax group 0 / 1, one query row per thread: whole S row to registers in
+//               one tcgen05.ld pass, exp2 against a reference max that is only moved when the
+//               row max grows by more than 2^8 (then O in TMEM and l are rescaled, rare),
+//               P -> bf16 -> 128B-swizzled smem for the PV MMA.
+__global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
     using S = AttnSmem;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -53,17 +84,15 @@ __global__ void __launch_bounds__(192, 1) attention_tc_kernel(const __grid_const
     uint64_t* k_empty = k_full + AT_KST;
     uint64_t* v_full = k_empty + AT_KST;
     uint64_t* v_empty = v_full + AT_KST;
-    uint64_t* s_full = v_empty + AT_KST;    // 2
-    uint64_t* s_empty = s_full + 2;
-    uint64_t* p_full = s_empty + 2;
-    uint64_t* p_empty = p_full + 2;
-    uint64_t* o_full = p_empty + 2;
-    uint64_t* o_empty = o_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+    uint64_t* s_full = v_empty + AT_KST;    // per group
+    uint64_t* s_empty = s_full + AT_QT;
+    uint64_t* p_full = s_empty + AT_QT;
+    uint64_t* p_empty = p_full + AT_QT;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + AT_QT);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * AT_BM;
+    const int q0 = blockIdx.x * (AT_BM * AT_QT);
     const int h = blockIdx.y;
     const int b = blockIdx.z;
     int kv_len = p.kv_len != nullptr ? p.kv_len[b] : p.T;
@@ -81,13 +110,11 @@ __global__ void __launch_bounds__(192, 1) attention_tc_kernel(const __grid_const
             mbar_init(&v_full[i], 1);
             mbar_init(&v_empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < AT_QT; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&s_empty[i], 128);
             mbar_init(&p_full[i], 128);
             mbar_init(&p_empty[i], 1);
-            mbar_init(&o_full[i], 1);
-            mbar_init(&o_empty[i], 128);
         }
         mbar_fence_init();
     }
@@ -99,13 +126,14 @@ __global__ void __launch_bounds__(192, 1) attention_tc_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base;          // 2 x 128 columns
-    const uint32_t tmem_O = tmem_base + 256;    // 2 x 64 columns
+    const uint32_t tmem_S = tmem_base;                    // AT_QT x 128 columns
+    const uint32_t tmem_O = tmem_base + AT_QT * AT_BN;    // AT_QT x 64 columns
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(q_full, S::TILE);
-            tma_load_3d(smem + S::Q_OFF, &p.qmap, q_full, h * AT_HD, q0, b);
+            mbar_expect_tx(q_full, AT_QT * S::TILE);
+            for (int g = 0; g < AT_QT; ++g)
+                tma_load_3d(smem + S::Q_OFF + g * S::TILE, &p.qmap, q_full, h * AT_HD, q0 + g * AT_BM, b);
             for (int j = 0; j < n_blocks; ++j) {
                 const int st = j % AT_KST;
                 const uint32_t ph = (j / AT_KST) & 1;
@@ -123,157 +151,152 @@ __global__ void __launch_bounds__(192, 1) attention_tc_kernel(const __grid_const
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
             const uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_HD, 0, 1);   // B (=V) MN-major
-            const uint32_t sq = smem_u32(smem + S::Q_OFF);
-            auto issue_s = [&](int j) {
-                const int st = j % AT_KST, sb = j & 1;
+            auto issue_s = [&](int g, int j) {
+                const int st = j % AT_KST;
                 mbar_wait(&k_full[st], (j / AT_KST) & 1);
-                mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
+                mbar_wait(&s_empty[g], (j & 1) ^ 1);          // softmax g has read S_g(j-1)
                 tc_fence_after();
+                const uint32_t sq = smem_u32(smem + S::Q_OFF + g * S::TILE);
                 const uint32_t sk = smem_u32(smem + S::K_OFF + st * S::TILE);
 #pragma unroll
                 for (int k = 0; k < AT_HD / 16; ++k)
-                    tc_mma_f16(tmem_S + sb * AT_BN, umma_desc_sw128(sq + k * 32, 0, 1024),
+                    tc_mma_f16(tmem_S + g * AT_BN, umma_desc_sw128(sq + k * 32, 0, 1024),
                                umma_desc_sw128(sk + k * 32, 0, 1024), idesc_s, k != 0);
-                tc_commit(&k_empty[st]);
-                tc_commit(&s_full[sb]);
+                tc_commit(&s_full[g]);
+                if (g == AT_QT - 1) tc_commit(&k_empty[st]);
             };
-            mbar_wait(q_full, 0);
-            issue_s(0);
-            for (int j = 0; j < n_blocks; ++j) {
-                if (j + 1 < n_blocks) issue_s(j + 1);
-                const int st = j % AT_KST, pb = j & 1;
+            auto issue_pv = [&](int g, int j) {
+                const int st = j % AT_KST;
                 mbar_wait(&v_full[st], (j / AT_KST) & 1);
-                mbar_wait(&o_empty[pb], ((j >> 1) & 1) ^ 1);
-                mbar_wait(&p_full[pb], (j >> 1) & 1);
+                mbar_wait(&p_full[g], j & 1);
                 tc_fence_after();
-                const uint32_t sp = smem_u32(smem + S::P_OFF + pb * 2 * S::TILE);
+                const uint32_t sp = smem_u32(smem + S::P_OFF + g * 2 * S::TILE);
                 const uint32_t sv = smem_u32(smem + S::V_OFF + st * S::TILE);
 #pragma unroll
                 for (int k = 0; k < AT_BN / 16; ++k) {
                     const uint64_t da = umma_desc_sw128(sp + (k >> 2) * S::TILE + (k & 3) * 32, 0, 1024);
                     const uint64_t db = umma_desc_mn_sw128(sv + k * 2048);
-                    tc_mma_f16(tmem_O + pb * AT_HD, da, db, idesc_o, k != 0);
+                    tc_mma_f16(tmem_O + g * AT_HD, da, db, idesc_o, (j | k) != 0);
                 }
-                tc_commit(&v_empty[st]);
-                tc_commit(&p_empty[pb]);
-                tc_commit(&o_full[pb]);
+                tc_commit(&p_empty[g]);
+                if (g == AT_QT - 1) tc_commit(&v_empty[st]);
+            };
+            mbar_wait(q_full, 0);
+            for (int g = 0; g < AT_QT; ++g) issue_s(g, 0);
+            for (int j = 0; j < n_blocks; ++j) {
+                for (int g = 0; g < AT_QT; ++g) {
+                    issue_pv(g, j);
+                    if (j + 1 < n_blocks) issue_s(g, j + 1);
+                }
             }
         }
     } else {
-        // ===================== softmax / output: one query row per thread =====================
+        // ===================== softmax groups: one query row per thread =====================
+        const int g = (warp - 2) >> 2;
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
+        const uint32_t tS = tmem_S + g * AT_BN + lane_addr;
+        const uint32_t tO = tmem_O + g * AT_HD + lane_addr;
         constexpr float kLog2e = 1.4426950408889634f;
-        float o_acc[AT_HD];
-#pragma unroll
-        for (int d = 0; d < AT_HD; ++d) o_acc[d] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+        constexpr float kThresh = 8.0f;       // in log2 units
+        uint8_t* pbuf = smem + S::P_OFF + g * 2 * S::TILE + row * 128;
+        float m_ref = 0.f, l_run = 0.f;       // m_ref in log2 units (already * log2e)
 
         for (int j = 0; j < n_blocks; ++j) {
-            const int sb = j & 1;
-            mbar_wait(&s_full[sb], (j >> 1) & 1);
+            mbar_wait(&s_full[g], j & 1);
             tc_fence_after();
+            uint32_t s[4][32];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, s[c]);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&s_empty[g]);
             const int kbase = j * AT_BN;
-            // pass 1: row max
-            float m_blk = -INFINITY;
+            if (kbase + AT_BN > kv_len) {     // only the last block has masked keys
 #pragma unroll
-            for (int c = 0; c < AT_BN; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_S + sb * AT_BN + lane_addr + c, r);
-                tc_wait_ld();
+                for (int c = 0; c < 4; ++c)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float s = (kbase + c + i < kv_len) ? __uint_as_float(r[i]) : -INFINITY;
-                    m_blk = fmaxf(m_blk, s);
-                }
+                    for (int i = 0; i < 32; ++i)
+                        if (kbase + c * 32 + i >= kv_len) s[c][i] = 0xff800000u;   // -inf
             }
-            const float m_new = fmaxf(m_run, m_blk);       // finite: block has >= 1 valid key
-            const float alpha = exp2f((m_run - m_new) * kLog2e);
-            const float mscaled = m_new * kLog2e;
-            // P buffer must be free (PV of block j-2 retired)
-            mbar_wait(&p_empty[sb], ((j >> 1) & 1) ^ 1);
-            uint8_t* pbuf = smem + S::P_OFF + sb * 2 * S::TILE;
-            float l_blk = 0.f;
+            float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < AT_BN; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_S + sb * AT_BN + lane_addr + c, r);
-                tc_wait_ld();
-                uint32_t packed[16];
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
+            mx *= kLog2e;
+            bool need = false;
+            float m_new = m_ref;
+            if (j == 0) {
+                m_new = mx;
+            } else if (mx > m_ref + kThresh) {
+                need = true;
+                m_new = mx;
+            }
+            float l_blk = 0.f;
+            uint32_t pk[64];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float p0 = (kbase + c + i < kv_len)
-                                   ? exp2f(fmaf(__uint_as_float(r[i]), kLog2e, -mscaled)) : 0.f;
-                    float p1 = (kbase + c + i + 1 < kv_len)
-                                   ? exp2f(fmaf(__uint_as_float(r[i + 1]), kLog2e, -mscaled)) : 0.f;
-                    // sum what the MMA will see (bf16-rounded), like flash kernels do not; keep fp32
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(s[c][i]), kLog2e, -m_new));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(s[c][i + 1]), kLog2e, -m_new));
                     l_blk += p0 + p1;
-                    packed[i >> 1] = pack_bf16(p0, p1);
+                    pk[c * 16 + (i >> 1)] = pack_bf16(p0, p1);
                 }
-                // 32 keys = 4 chunks of 16 B; tile = c / 64, chunk index within the 128 B row
-                uint8_t* tile = pbuf + (c >> 6) * S::TILE + row * 128;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int chunk = ((c & 63) >> 3) + q;
-                    uint4 val = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2],
-                                           packed[4 * q + 3]);
-                    *reinterpret_cast<uint4*>(tile + ((chunk ^ (row & 7)) << 4)) = val;
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&s_empty[sb]);
-            fence_proxy_async_smem();
-            mbar_arrive(&p_full[sb]);
-            l_run = l_run * alpha + l_blk;
-            m_run = m_new;
-            // fold in the previous block's PV product (had a whole iteration to finish)
-            if (j > 0) {
-                const int ob = (j - 1) & 1;
-                mbar_wait(&o_full[ob], ((j - 1) >> 1) & 1);
+            // PV of the previous block must have retired before P / O are touched
+            mbar_wait(&p_empty[g], (j & 1) ^ 1);
+            if (__any_sync(0xffffffffu, need)) {
                 tc_fence_after();
+                const float alpha = need ? fast_exp2(m_ref - m_new) : 1.0f;
+                l_run *= alpha;
 #pragma unroll
                 for (int c = 0; c < AT_HD; c += 32) {
                     uint32_t r[32];
-                    tmem_ld_32x32(tmem_O + ob * AT_HD + lane_addr + c, r);
+                    tmem_ld_32x32(tO + c, r);
                     tc_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        o_acc[c + i] = fmaf(o_acc[c + i], alpha_prev, __uint_as_float(r[i]));
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                    tmem_st_32x32(tO + c, r);
                 }
-                tc_fence_before();
-                mbar_arrive(&o_empty[ob]);
+                tc_wait_st();
             }
-            alpha_prev = alpha;
-        }
-        {
-            const int j = n_blocks - 1;
-            const int ob = j & 1;
-            mbar_wait(&o_full[ob], (j >> 1) & 1);
-            tc_fence_after();
+            m_ref = m_new;
+            l_run += l_blk;
+            // P row: 128 keys = 2 tiles x 8 chunks of 16 B, 128B-swizzled (chunk ^ (row & 7))
 #pragma unroll
-            for (int c = 0; c < AT_HD; c += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_O + ob * AT_HD + lane_addr + c, r);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    o_acc[c + i] = fmaf(o_acc[c + i], alpha_prev, __uint_as_float(r[i]));
+            for (int q = 0; q < 16; ++q) {
+                uint8_t* tile = pbuf + (q >> 3) * S::TILE;
+                *reinterpret_cast<uint4*>(tile + (((q & 7) ^ (row & 7)) << 4)) =
+                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
             }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&p_full[g]);
         }
-        const int t = q0 + row;
-        if (t < p.T) {
-            const float inv_l = 1.0f / l_run;
-            __nv_bfloat16* o = p.out + static_cast<long long>(b) * p.o_bstride +
-                               static_cast<long long>(t) * p.o_rstride + h * AT_HD;
+        // last PV retired -> O complete
+        mbar_wait(&p_empty[g], (n_blocks - 1) & 1);
+        tc_fence_after();
+        const int t = q0 + g * AT_BM + row;
+        const float inv_l = 1.0f / l_run;
+        __nv_bfloat16* o = p.out + static_cast<long long>(b) * p.o_bstride +
+                           static_cast<long long>(t) * p.o_rstride + h * AT_HD;
 #pragma unroll
-            for (int d = 0; d < AT_HD; d += 8) {
-                uint4 q;
-                q.x = pack_bf16(o_acc[d] * inv_l, o_acc[d + 1] * inv_l);
-                q.y = pack_bf16(o_acc[d + 2] * inv_l, o_acc[d + 3] * inv_l);
-                q.z = pack_bf16(o_acc[d + 4] * inv_l, o_acc[d + 5] * inv_l);
-                q.w = pack_bf16(o_acc[d + 6] * inv_l, o_acc[d + 7] * inv_l);
-                *reinterpret_cast<uint4*>(o + d) = q;
+        for (int c = 0; c < AT_HD; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tO + c, r);
+            tc_wait_ld();
+            if (t < p.T) {
+#pragma unroll
+                for (int d = 0; d < 32; d += 8) {
+                    uint4 q;
+                    q.x = pack_bf16(__uint_as_float(r[d]) * inv_l, __uint_as_float(r[d + 1]) * inv_l);
+                    q.y = pack_bf16(__uint_as_float(r[d + 2]) * inv_l, __uint_as_float(r[d + 3]) * inv_l);
+                    q.z = pack_bf16(__uint_as_float(r[d + 4]) * inv_l, __uint_as_float(r[d + 5]) * inv_l);
+                    q.w = pack_bf16(__uint_as_float(r[d + 6]) * inv_l, __uint_as_float(r[d + 7]) * inv_l);
+                    *reinterpret_cast<uint4*>(o + c + d) = q;
+                }
             }
         }
     }
@@ -385,8 +408,8 @@ extern "C" int svc_attention(const void* q, const void* k, const void* v, long l
                                  AttnSmem::TOTAL);
             attr_set = true;
         }
-        dim3 grid((T + AT_BM - 1) / AT_BM, H, B);
-        attention_tc_kernel<<<grid, 192, AttnSmem::TOTAL, st>>>(p);
+        dim3 grid((T + AT_BM * AT_QT - 1) / (AT_BM * AT_QT), H, B);
+        attention_tc_kernel<<<grid, AT_THREADS, AttnSmem::TOTAL, st>>>(p);
         SVC_CHECK_LAUNCH();
         return SVC_OK;
     }

@@ -63,7 +63,9 @@ inline EpiParams make_epi_params(const svc_gemm_desc& d) {
     const int osz = e.op_is_f32 ? 4 : 2;
     e.vec_ok = al(d.res, d.res_bstride, d.res_rstride, 4) &&
                al(d.out_f32, d.of_bstride, d.of_rstride, 4) &&
-               al(d.out_op, d.oo_bstride, d.oo_rstride, osz) && (e.N_out % 8 == 0);
+               al(d.out_op, d.oo_bstride, d.oo_rstride, osz) && (e.N_out % 8 == 0) &&
+               al(d.bias, 0, 0, 4) && al(d.rowbias, d.rowbias_bstride, 0, 4) &&
+               al(d.gate, d.gate_bstride, 0, 4) && al(d.rope_tab, 0, 0, 4);
     return e;
 }
 

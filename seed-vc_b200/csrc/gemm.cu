@@ -10,6 +10,7 @@
 //
 // Reference sites replaced: nn.Linear / nn.Conv1d / nn.ConvTranspose1d calls listed in
 // include/seedvc_b200.h next to svc_gemm.
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -35,36 +36,266 @@ struct alignas(64) TcParams {
     TcSeg seg[SVC_MAX_SEG];
     int n_seg, total_kb;
     int B, T, tiles_per_batch, n_tiles;
+    int dbg;   // SVC_DBG env: 1 = skip epilogue body, 2 = skip MMA issue (profiling experiments)
     EpiParams epi;
 };
+
+constexpr int kEpiWarps = 8;             // two epilogue groups of 4 warps (one per TMEM buffer)
+constexpr int kTcThreads = 64 + kEpiWarps * 32;    // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kStageRowF = 32;           // fp32 row of the per-warp transpose buffer (XOR-swizzled)
 
 template <int BN, int STAGES>
 struct TcSmem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int EPI_BYTES = kEpiWarps * 32 * kStageRowF * 4;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+    static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
+// Epilogue of one 32-row x 32-column accumulator chunk, executed by one warp.
+//   prefetch (lane = 4 columns x 1 row per step): residual / accumulate inputs, issued before
+//            the accumulator is even read so their latency hides behind phase 1
+//   phase 1 (thread = row): bias, per-batch bias, activation (pairs / RoPE need adjacent columns)
+//   transpose through an XOR-swizzled smem tile (float4 both ways, conflict free)
+//   phase 2 (lane = 4 columns): gate, residual, alpha, accumulate and the stores - every global
+//            access is a contiguous row segment (coalesced 16 B per lane).
+// bf16-output tensor-core path: approximate transcendentals (1 MUFU each) are far below the
+// 2^-9 output rounding; the fp32 SIMT path keeps the precise versions (epilogue.cuh).
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct EpiChunk {
+    int co, c0;        // outputs per row in this chunk (32, or 16 after a pair activation), first column
+    int lanes_per_row; // co / 4
+    int rows_per_it;   // 32 / lanes_per_row
+    int n_it;          // 32 / rows_per_it
+    bool vec;          // vector path usable for this chunk
+};
+
+__device__ __forceinline__ EpiChunk epi_chunk_geom(const EpiParams& e, int n0) {
+    EpiChunk g;
+    const bool pair = e.act == SVC_ACT_SWIGLU_PAIR || e.act == SVC_ACT_TANH_SIG_PAIR;
+    g.co = pair ? 16 : 32;
+    g.c0 = pair ? (n0 >> 1) : n0;
+    g.lanes_per_row = g.co >> 2;
+    g.rows_per_it = 32 / g.lanes_per_row;
+    g.n_it = 32 / g.rows_per_it;
+    g.vec = e.vec_ok && (g.c0 + g.co <= e.N_out) && !(e.act == SVC_ACT_ROPE && e.res != nullptr);
+    return g;
+}
+
+// rr[it] <- raw residual (or, without a residual, the old output when accumulating) for the 4
+// columns this lane owns in step `it` (vector path only).  The values are NOT touched here: any
+// arithmetic on them would stall the warp until the loads land and defeat the prefetch.
+__device__ __forceinline__ void epi_prefetch(const EpiParams& e, const EpiChunk& g, int lane, int b,
+                                             int t_base, int T, float4 (&rr)[8]) {
+    const int c = g.c0 + (lane % g.lanes_per_row) * 4;
+    const int rsub = lane / g.lanes_per_row;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int t = t_base + it * g.rows_per_it + rsub;
+        if (it < g.n_it && t < T) {
+            if (e.act == SVC_ACT_ROPE) {
+                if (c < e.rope_cols)      // (cos, sin) of the two pairs this lane owns, coalesced
+                    rr[it] = __ldg(reinterpret_cast<const float4*>(
+                        e.rope_tab + static_cast<long long>(e.rope_pos0 + t) * 64 + (c & 63)));
+            } else if (e.res != nullptr)
+                rr[it] = __ldg(reinterpret_cast<const float4*>(
+                    e.res + static_cast<long long>(b) * e.res_bstride +
+                    static_cast<long long>(t) * e.res_rstride + c));
+            else if (e.accumulate)
+                rr[it] = *reinterpret_cast<const float4*>(
+                    e.out_f32 + static_cast<long long>(b) * e.of_bstride +
+                    static_cast<long long>(t) * e.of_rstride + c);
+        }
+    }
+}
+
+__device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& e, const EpiChunk& g,
+                                                         float* stage, int lane, int b, int t_base,
+                                                         int T, int n0, float (&v)[32],
+                                                         const float4 (&rr)[8], int dbg) {
+    const int t_row = t_base + lane;
+    // linear epilogues (no activation, or RoPE) add the biases after the transpose, 4 columns
+    // per lane; activations need them first
+    const bool bias_late = g.vec && (e.act == SVC_ACT_NONE || e.act == SVC_ACT_ROPE);
+    if (dbg & 4) goto transpose;
+    if (e.bias != nullptr && !bias_late) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (n0 + j < e.N) v[j] += __ldg(e.bias + n0 + j);
+    }
+    if (e.rowbias != nullptr && !bias_late) {
+        const float* rb = e.rowbias + static_cast<long long>(b) * e.rowbias_bstride;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (n0 + j < e.N) v[j] += __ldg(rb + n0 + j);
+    }
+    if (e.act == SVC_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(v[j]);
+    } else if (e.act == SVC_ACT_SWIGLU_PAIR) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * fast_sigmoid(v[2 * j]) * v[2 * j + 1];
+    } else if (e.act == SVC_ACT_TANH_SIG_PAIR) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fast_tanh(v[2 * j]) * fast_sigmoid(v[2 * j + 1]);
+    } else if (e.act == SVC_ACT_ROPE && !g.vec) {
+        if (n0 < e.rope_cols && t_row < T) {
+            const float* tab = e.rope_tab + static_cast<long long>(e.rope_pos0 + t_row) * 64;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int i = ((n0 + 2 * j) & 63) >> 1;
+                const float2 cs = __ldg(reinterpret_cast<const float2*>(tab) + i);
+                const float x0 = v[2 * j], x1 = v[2 * j + 1];
+                v[2 * j] = x0 * cs.x - x1 * cs.y;
+                v[2 * j + 1] = x1 * cs.x + x0 * cs.y;
+            }
+        }
+        if (n0 < e.q_cols) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= e.q_scale;
+        }
+    }
+transpose:
+    // ---- transpose: row-per-thread -> 4-columns-per-lane (slot q of row r lives at q ^ (r & 7))
+    if (dbg & 16) return;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (q < g.lanes_per_row)
+            *reinterpret_cast<float4*>(stage + lane * kStageRowF + ((q ^ (lane & 7)) << 2)) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    __syncwarp();
+    const int q = lane % g.lanes_per_row;
+    const int rsub = lane / g.lanes_per_row;
+    const int c = g.c0 + q * 4;
+    if (dbg & 8) return;
+    if (g.vec) {
+        float4 gt = make_float4(e.alpha, e.alpha, e.alpha, e.alpha);
+        const bool is_rope = e.act == SVC_ACT_ROPE;
+        const bool rope = is_rope && c < e.rope_cols;
+        const float qs = (is_rope && c < e.q_cols) ? e.q_scale : 1.0f;
+        const bool has_rr = !is_rope && (e.res != nullptr || e.accumulate);
+        const float rr_scale = e.res != nullptr ? e.alpha : 1.0f;
+        const bool rmw = e.res != nullptr && e.accumulate;
+        float4 bl = make_float4(0.f, 0.f, 0.f, 0.f);     // late biases for this lane's 4 columns
+        if (bias_late) {
+            if (e.bias != nullptr) bl = __ldg(reinterpret_cast<const float4*>(e.bias + c));
+            if (e.rowbias != nullptr) {
+                const float4 rb4 = __ldg(reinterpret_cast<const float4*>(
+                    e.rowbias + static_cast<long long>(b) * e.rowbias_bstride + c));
+                bl.x += rb4.x, bl.y += rb4.y, bl.z += rb4.z, bl.w += rb4.w;
+            }
+        }
+        if (e.gate != nullptr) {
+            const float4 gq = __ldg(reinterpret_cast<const float4*>(
+                e.gate + static_cast<long long>(b) * e.gate_bstride + c));
+            gt.x *= gq.x, gt.y *= gq.y, gt.z *= gq.z, gt.w *= gq.w;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * g.rows_per_it + rsub;
+            const int t = t_base + r;
+            if (it < g.n_it && t < T) {
+                float4 a = *reinterpret_cast<const float4*>(stage + r * kStageRowF + ((q ^ (r & 7)) << 2));
+                a.x += bl.x, a.y += bl.y, a.z += bl.z, a.w += bl.w;
+                if (rope) {
+                    const float4 cs = rr[it];
+                    const float y0 = a.x * cs.x - a.y * cs.y, y1 = a.y * cs.x + a.x * cs.y;
+                    const float y2 = a.z * cs.z - a.w * cs.w, y3 = a.w * cs.z + a.z * cs.w;
+                    a = make_float4(y0 * qs, y1 * qs, y2 * qs, y3 * qs);
+                }
+                float4 x = make_float4(a.x * gt.x, a.y * gt.y, a.z * gt.z, a.w * gt.w);
+                if (has_rr) {
+                    x.x = fmaf(rr[it].x, rr_scale, x.x), x.y = fmaf(rr[it].y, rr_scale, x.y);
+                    x.z = fmaf(rr[it].z, rr_scale, x.z), x.w = fmaf(rr[it].w, rr_scale, x.w);
+                }
+                float* of = e.out_f32 + static_cast<long long>(b) * e.of_bstride +
+                            static_cast<long long>(t) * e.of_rstride + c;
+                if (rmw) {                       // residual AND accumulate: old value read here
+                    const float4 o = *reinterpret_cast<const float4*>(of);
+                    x.x += o.x, x.y += o.y, x.z += o.z, x.w += o.w;
+                }
+                if (e.out_f32 != nullptr) *reinterpret_cast<float4*>(of) = x;
+                if (e.out_op != nullptr) {
+                    const long long off = static_cast<long long>(b) * e.oo_bstride +
+                                          static_cast<long long>(t) * e.oo_rstride + c;
+                    if (e.op_is_f32) {
+                        *reinterpret_cast<float4*>(static_cast<float*>(e.out_op) + off) = x;
+                    } else {
+                        uint2 pk;
+                        pk.x = pack_bf16(x.x, x.y);
+                        pk.y = pack_bf16(x.z, x.w);
+                        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(e.out_op) + off) = pk;
+                    }
+                }
+            }
+        }
+    } else {
+        // scalar fallback (unaligned views or a partial last chunk): still row-contiguous
+        for (int it = 0; it < g.n_it; ++it) {
+            const int r = it * g.rows_per_it + rsub;
+            const int t = t_base + r;
+            if (t >= T) break;
+            for (int k = 0; k < 4; ++k) {
+                const int cc = c + k;
+                if (cc >= e.N_out) break;
+                float x = stage[r * kStageRowF + ((q ^ (r & 7)) << 2) + k];
+                if (e.gate != nullptr) x *= __ldg(e.gate + static_cast<long long>(b) * e.gate_bstride + cc);
+                if (e.res != nullptr)
+                    x += __ldg(e.res + static_cast<long long>(b) * e.res_bstride +
+                               static_cast<long long>(t) * e.res_rstride + cc);
+                x *= e.alpha;
+                if (e.out_f32 != nullptr) {
+                    float* o = e.out_f32 + static_cast<long long>(b) * e.of_bstride +
+                               static_cast<long long>(t) * e.of_rstride + cc;
+                    if (e.accumulate) x += *o;
+                    *o = x;
+                }
+                if (e.out_op != nullptr) {
+                    const long long off = static_cast<long long>(b) * e.oo_bstride +
+                                          static_cast<long long>(t) * e.oo_rstride + cc;
+                    if (e.op_is_f32) static_cast<float*>(e.out_op)[off] = x;
+                    else static_cast<__nv_bfloat16*>(e.out_op)[off] = __float2bfloat16_rn(x);
+                }
+            }
+        }
+    }
+}
+
+// Persistent, warp-specialised tcgen05 GEMM.  One CTA per SM walks output tiles
+// (n fastest, so CTAs running together share the A tile in L2); the accumulator is
+// double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
     using S = TcSmem<BN, STAGES>;
+    constexpr int ACC_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x % p.n_tiles;
-    const int m_tile = blockIdx.x / p.n_tiles;
-    const int b = m_tile / p.tiles_per_batch;
-    const int t0 = (m_tile % p.tiles_per_batch) * BM;
-    const int n0 = n_tile * BN;
+    const int total_tiles = p.B * p.tiles_per_batch * p.n_tiles;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < kMaxMaps; ++i) {
@@ -75,11 +306,14 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], kEpiWarps / 2);
+        }
         mbar_fence_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, BN);
+        tmem_alloc(tmem_slot, 2 * ACC_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -92,20 +326,26 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int s = 0; s < p.n_seg; ++s) {
-                const TcSeg sg = p.seg[s];
-                for (int kb = 0; kb < sg.nkb; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-                    uint8_t* sa = smem + stage * S::STAGE_BYTES;
-                    tma_load_3d(sa, &p.amap[sg.a_map], &full_bar[stage], kb * BK, t0 + sg.shift, b);
-                    // weight maps are rank 3 too (K, rows, 1): the TMA instruction rank must
-                    // match the tensor-map rank
-                    tma_load_3d(sa + S::A_BYTES, &p.wmap[sg.w_map], &full_bar[stage], kb * BK,
-                                sg.w_row0 + n0, 0);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        phase ^= 1;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                const int m_tile = tile / p.n_tiles;
+                const int b = m_tile / p.tiles_per_batch;
+                const int t0 = (m_tile % p.tiles_per_batch) * BM;
+                const int n0 = n_tile * BN;
+                for (int s = 0; s < p.n_seg; ++s) {
+                    const TcSeg sg = p.seg[s];
+                    for (int kb = 0; kb < sg.nkb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                        uint8_t* sa = smem + stage * S::STAGE_BYTES;
+                        tma_load_3d(sa, &p.amap[sg.a_map], &full_bar[stage], kb * BK, t0 + sg.shift, b);
+                        // weight maps are rank 3 too (K, rows, 1): instruction rank == map rank
+                        tma_load_3d(sa + S::A_BYTES, &p.wmap[sg.w_map], &full_bar[stage], kb * BK,
+                                    sg.w_row0 + n0, 0);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
                 }
             }
@@ -113,53 +353,112 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ Tc
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            int n_umma = p.epi.N - n0;
-            n_umma = n_umma > BN ? BN : ((n_umma + 15) & ~15);
-            const uint32_t idesc = umma_idesc_bf16(BM, n_umma, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < p.total_kb; ++it) {
-                mbar_wait(&full_bar[stage], phase);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int n0 = (tile % p.n_tiles) * BN;
+                int n_umma = p.epi.N - n0;
+                n_umma = n_umma > BN ? BN : ((n_umma + 15) & ~15);
+                const uint32_t idesc = umma_idesc_bf16(BM, n_umma, 0, 0);
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);   // epilogue drained this buffer
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-                const uint32_t sb = sa + S::A_BYTES;
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                for (int kb = 0; kb < p.total_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+                    const uint32_t sb = sa + S::A_BYTES;
+                    if (!(p.dbg & 2)) {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t da = umma_desc_sw128(sa + k * 32, 0, 1024);
-                    const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
-                    tc_mma_f16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da = umma_desc_sw128(sa + k * 32, 0, 1024);
+                            const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
+                            tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
-                tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                if (++stage == STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+                tc_commit(&tmem_full_bar[acc]);
             }
-            tc_commit(tmem_full_bar);
         }
     } else {
-        // ===================== epilogue =====================
-        const int lg = warp & 3;  // TMEM lane group this warp may access
-        const int row = lg * 32 + lane;
-        const int t = t0 + row;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const int ncols = min(BN, p.epi.N - n0);
-        for (int c = 0; c < ncols; c += 32) {
+        // ===================== epilogue: group g (4 warps) owns TMEM buffer g =====================
+        // Tiles alternate between the two groups, so each group has two mainloop durations to
+        // drain its accumulator.  Work items are (tile, 32-column chunk); the residual /
+        // accumulate inputs of item k+1 are requested before item k is processed, so global
+        // loads stay in flight the whole time.
+        const int ew = warp - 2;
+        const int group = ew >> 2;
+        const int lg = warp & 3;             // TMEM lane group this warp may access
+        float* stage_buf = reinterpret_cast<float*>(smem + S::EPI_OFFSET) + ew * 32 * kStageRowF;
+        const uint32_t taddr = tmem_base + group * ACC_COLS + (static_cast<uint32_t>(lg * 32) << 16);
+        struct Item {
+            int it, ch, b, t_base, n0c;
+            bool valid, last;
+        };
+        auto make_item = [&](int it, int ch) {
+            Item x;
+            x.it = it;
+            x.ch = ch;
+            const int tile = blockIdx.x + it * gridDim.x;
+            x.valid = tile < total_tiles;
+            x.b = 0, x.t_base = 0, x.n0c = 0, x.last = true;
+            if (x.valid) {
+                const int n_tile = tile % p.n_tiles;
+                const int m_tile = tile / p.n_tiles;
+                x.b = m_tile / p.tiles_per_batch;
+                x.t_base = (m_tile % p.tiles_per_batch) * BM + lg * 32;
+                const int n0 = n_tile * BN;
+                x.n0c = n0 + ch * 32;
+                x.last = (ch + 1) * 32 >= min(BN, p.epi.N - n0);
+            }
+            return x;
+        };
+        Item cur = make_item(group, 0);
+        EpiChunk g_cur = epi_chunk_geom(p.epi, cur.n0c);
+        float4 rr_cur[8], rr_nxt[8];
+        if (cur.valid && g_cur.vec && cur.t_base < p.T)
+            epi_prefetch(p.epi, g_cur, lane, cur.b, cur.t_base, p.T, rr_cur);
+        while (cur.valid) {
+            if (cur.ch == 0) {
+                mbar_wait(&tmem_full_bar[group], (cur.it >> 1) & 1);
+                tc_fence_after();
+            }
             uint32_t r[32];
-            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c, r);
+            tmem_ld_32x32(taddr + cur.ch * 32, r);
+            const Item nxt = cur.last ? make_item(cur.it + 2, 0) : make_item(cur.it, cur.ch + 1);
+            const EpiChunk g_nxt = epi_chunk_geom(p.epi, nxt.n0c);
+            if (nxt.valid && g_nxt.vec && nxt.t_base < p.T)
+                epi_prefetch(p.epi, g_nxt, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
             tc_wait_ld();
+            if (cur.last) {                     // this warp has read its whole slice of the buffer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
+            }
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (t < p.T) epilogue_chunk<32>(p.epi, b, t, n0 + c, v);
+            if (cur.t_base < p.T && !(p.dbg & 1))
+                epilogue_chunk_coalesced(p.epi, g_cur, stage_buf, lane, cur.b, cur.t_base, p.T, cur.n0c,
+                                         v, rr_cur, p.dbg);
+            cur = nxt;
+            g_cur = g_nxt;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rr_cur[i] = rr_nxt[i];
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, 2 * ACC_COLS);
     }
 }
 
@@ -290,7 +589,9 @@ static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
                              S::TOTAL);
         attr_set = true;
     }
-    gemm_tc_kernel<BN, STAGES><<<m_tiles * p.n_tiles, 192, S::TOTAL, stream>>>(p);
+    const int tiles = m_tiles * p.n_tiles;
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    gemm_tc_kernel<BN, STAGES><<<grid, kTcThreads, S::TOTAL, stream>>>(p);
     SVC_CHECK_LAUNCH();
     return SVC_OK;
 }
@@ -302,7 +603,7 @@ static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
     if (d.N <= 32) BN = 32;
     else if (d.N <= 64) BN = 64;
     else if (d.N <= 128) BN = 128;
-    else if (d.N % 256 == 0 || d.N > 1024) BN = 256;
+    else BN = 256;
     // ---- A maps: one per distinct view ---------------------------------------------------
     struct AKey { const void* ptr; long long bs, rs; int rows, K; };
     AKey akeys[kMaxMaps];
@@ -355,6 +656,8 @@ static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
             return SVC_ERR_ARG;
         }
     }
+    static const int dbg = getenv("SVC_DBG") ? atoi(getenv("SVC_DBG")) : 0;
+    p.dbg = dbg;
     p.n_seg = d.n_seg;
     p.total_kb = total_kb;
     p.B = d.B;
@@ -364,9 +667,9 @@ static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
     p.epi = make_epi_params(d);
     const int m_tiles = d.B * p.tiles_per_batch;
     switch (BN) {
-        case 32: return launch_tc<32, 4>(p, m_tiles, stream);
-        case 64: return launch_tc<64, 4>(p, m_tiles, stream);
-        case 128: return launch_tc<128, 3>(p, m_tiles, stream);
+        case 32: return launch_tc<32, 8>(p, m_tiles, stream);
+        case 64: return launch_tc<64, 8>(p, m_tiles, stream);
+        case 128: return launch_tc<128, 6>(p, m_tiles, stream);
         default: return launch_tc<256, 4>(p, m_tiles, stream);
     }
 }

@@ -228,6 +228,17 @@ class DiTEngine:
             w["wn"] = wn
             w["wn_cond_w"] = dev(torch.cat(cws, 0))                            # (nl*2Dw, Dw) fp32
             w["wn_cond_b"] = dev(torch.cat(cbs, 0))
+            # skip path of all layers as ONE contraction over the concatenated gated activations:
+            # output = sum_l acts_l @ W_skip_l^T (+ res_projection as a second segment)
+            skip_w, skip_b = [], sd[p + "res_projection.bias"].float().clone()
+            for l in range(nl):
+                wr = _fold_wn(sd, f"{p}wavenet.res_skip_layers.{l}.conv.conv")
+                wr = wr.reshape(wr.shape[0], Dw)
+                br = sd[f"{p}wavenet.res_skip_layers.{l}.conv.conv.bias"].float()
+                skip_w.append(wr[Dw:] if l < nl - 1 else wr)
+                skip_b += br[Dw:] if l < nl - 1 else br
+            w["wn_skip_w"] = dev(torch.cat(skip_w, 1), od)                     # (Dw, nl*Dw)
+            w["wn_skip_b"] = dev(skip_b)
         self.w = w
 
     def setup_rope(self, n_pos, device):
@@ -371,7 +382,7 @@ class DiTEngine:
             Dw, pad = sp.Dw, (sp.wn_kernel - 1) // 2
             st["xw"] = torch.empty(R, T, Dw, dtype=f32, device=dev)
             st["xw_op"] = torch.zeros(R, T + 2 * pad, Dw, dtype=od, device=dev)
-            st["acts"] = torch.empty(R, T, Dw, dtype=od, device=dev)
+            st["acts"] = torch.empty(R, T, sp.wn_layers * Dw, dtype=od, device=dev)
             st["wn_out"] = torch.empty(R, T, Dw, dtype=f32, device=dev)
             st["ln"] = torch.empty(R, T, Dw, dtype=od, device=dev)
             st["y"] = torch.empty(R, T, Dw, dtype=od, device=dev)
@@ -483,22 +494,20 @@ class DiTEngine:
         body = xw_op[:, pad:pad + T, :]
         ops.gemm([(xr, 0, w["conv1_w"])], Dw, B=R, T=T, bias=w["conv1_b"], out_f32=xw, out_op=body)
         ops.reflect_halo(xw_op, T, pad, st["wn_lens"])
-        ops.gemm([(xr, 0, w["resp_w"])], Dw, B=R, T=T, bias=w["resp_b"], out_f32=wn_out)
         g_all = st["wn_g"][s]
         for l in range(nl):
             wl = w["wn"][l]
             g_l = g_all[l * 2 * Dw:(l + 1) * 2 * Dw].view(1, 2 * Dw).expand(R, 2 * Dw)
+            acts_l = acts[:, :, l * Dw:(l + 1) * Dw]
             segs = [(xw_op, j, wl["in_w"][j]) for j in range(ks)]
-            ops.gemm(segs, 2 * Dw, B=R, T=T, rowbias=g_l, act=ACT_TANH_SIG_PAIR, out_op=acts)
+            ops.gemm(segs, 2 * Dw, B=R, T=T, rowbias=g_l, act=ACT_TANH_SIG_PAIR, out_op=acts_l)
             if l < nl - 1:
-                ops.gemm([(acts, 0, wl["rs_w"][:Dw])], Dw, B=R, T=T, bias=wl["rs_b_res"],
+                ops.gemm([(acts_l, 0, wl["rs_w"][:Dw])], Dw, B=R, T=T, bias=wl["rs_b_res"],
                          res=xw, out_f32=xw, out_op=body)
                 ops.reflect_halo(xw_op, T, pad, st["wn_lens"])
-                ops.gemm([(acts, 0, wl["rs_w"][Dw:])], Dw, B=R, T=T, bias=wl["rs_b_skip"],
-                         accumulate=True, out_f32=wn_out)
-            else:
-                ops.gemm([(acts, 0, wl["rs_w"])], Dw, B=R, T=T, bias=wl["rs_b"], accumulate=True,
-                         out_f32=wn_out)
+        # output = sum_l skip_l + res_projection(x_res): one GEMM, K = nl*Dw + D, no accumulate passes
+        ops.gemm([(acts, 0, w["wn_skip_w"]), (xr, 0, w["resp_w"])], Dw, B=R, T=T, bias=w["wn_skip_b"],
+                 out_f32=wn_out)
         a = self._ada(s, "fl")                                   # shift, 1+scale
         ops.norm_mod(wn_out, st["ln"], mul=a[Dw:], add=a[:Dw], eps=1e-6, mode=1)
         ops.gemm([(st["ln"], 0, w["fl_w"])], Dw, B=R, T=T, bias=w["fl_b"], out_op=st["y"])
