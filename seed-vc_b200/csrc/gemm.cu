@@ -37,6 +37,10 @@ struct alignas(64) TcParams {
     int n_seg, total_kb;
     int B, T, tiles_per_batch, n_tiles;
     int dbg;   // SVC_DBG env: 1 = skip epilogue body, 2 = skip MMA issue (profiling experiments)
+    // TMA-store epilogue: 0 = off (register/LSU epilogue), 1 = bf16 tile -> out_op,
+    // 2 = fp32 tile reduce-added into out_f32 (in-place residual), 3 = fp32 tile -> out_f32
+    int store_mode;
+    CUtensorMap omap;          // (N_out, T, B) view of the output, box {32, 32, 1}, no swizzle
     EpiParams epi;
 };
 
@@ -277,10 +281,142 @@ transpose:
     }
 }
 
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* src, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+            reinterpret_cast<uint64_t>(tmap)),
+        "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// TMA-store epilogue of one item = 32 rows x 32 OUTPUT columns (32 accumulator columns, or 64 for
+// the pair activations), executed by one warp:
+//   phase 1 (thread = row): early biases + activation, fp32 tile into XOR-swizzled smem
+//   phase 2 (lane = 4 columns, registers): late biases, RoPE with coalesced prefetched table
+//            values, gate, alpha
+//   the finished tile goes back to smem in plain row-major output dtype and ONE elected lane
+//   hands it to the TMA unit (store, or fp32 reduce-add for the in-place residual update):
+//   no per-element address arithmetic, bounds handling by the tensor map, stores fully async.
+template <bool PAIR>
+__device__ __forceinline__ void epilogue_item_tma(const TcParams& p, float* stage, int lane, int b,
+                                                  int t_base, int n0_acc, float (&v)[PAIR ? 64 : 32],
+                                                  const float4 (&rr)[8]) {
+    const EpiParams& e = p.epi;
+    constexpr int NA = PAIR ? 64 : 32;
+    const int c0 = PAIR ? (n0_acc >> 1) : n0_acc;          // first output column
+    const bool bias_late = e.act == SVC_ACT_NONE || e.act == SVC_ACT_ROPE;
+    if (!bias_late) {
+        if (e.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NA; ++j)
+                if (n0_acc + j < e.N) v[j] += __ldg(e.bias + n0_acc + j);
+        }
+        if (e.rowbias != nullptr) {
+            const float* rb = e.rowbias + static_cast<long long>(b) * e.rowbias_bstride;
+#pragma unroll
+            for (int j = 0; j < NA; ++j)
+                if (n0_acc + j < e.N) v[j] += __ldg(rb + n0_acc + j);
+        }
+    }
+    if (e.act == SVC_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(v[j]);
+    } else if (PAIR && e.act == SVC_ACT_SWIGLU_PAIR) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[2 * j] * fast_sigmoid(v[2 * j]) * v[2 * j + 1];
+    } else if (PAIR && e.act == SVC_ACT_TANH_SIG_PAIR) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[2 * j]) * fast_sigmoid(v[2 * j + 1]);
+    }
+    // the previous TMA store of this warp must have finished reading the staging tile
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(stage + lane * kStageRowF + ((q ^ (lane & 7)) << 2)) =
+            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    __syncwarp();
+    const int q = lane & 7;
+    const int rsub = lane >> 3;
+    const int c = c0 + q * 4;
+    const bool is_rope = e.act == SVC_ACT_ROPE;
+    const bool rope = is_rope && c < e.rope_cols;
+    const float qs = (is_rope && c < e.q_cols) ? e.q_scale : 1.0f;
+    float4 gt = make_float4(e.alpha, e.alpha, e.alpha, e.alpha);
+    float4 bl = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < e.N_out) {
+        if (e.gate != nullptr) {
+            const float4 gq = __ldg(reinterpret_cast<const float4*>(
+                e.gate + static_cast<long long>(b) * e.gate_bstride + c));
+            gt.x *= gq.x, gt.y *= gq.y, gt.z *= gq.z, gt.w *= gq.w;
+        }
+        if (bias_late) {
+            if (e.bias != nullptr) bl = __ldg(reinterpret_cast<const float4*>(e.bias + c));
+            if (e.rowbias != nullptr) {
+                const float4 rb4 = __ldg(reinterpret_cast<const float4*>(
+                    e.rowbias + static_cast<long long>(b) * e.rowbias_bstride + c));
+                bl.x += rb4.x, bl.y += rb4.y, bl.z += rb4.z, bl.w += rb4.w;
+            }
+        }
+    }
+    float4 a[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rsub;
+        a[it] = *reinterpret_cast<const float4*>(stage + r * kStageRowF + ((q ^ (r & 7)) << 2));
+        a[it].x += bl.x, a[it].y += bl.y, a[it].z += bl.z, a[it].w += bl.w;
+        if (rope) {
+            const float4 cs = rr[it];
+            const float y0 = a[it].x * cs.x - a[it].y * cs.y, y1 = a[it].y * cs.x + a[it].x * cs.y;
+            const float y2 = a[it].z * cs.z - a[it].w * cs.w, y3 = a[it].w * cs.z + a[it].z * cs.w;
+            a[it] = make_float4(y0 * qs, y1 * qs, y2 * qs, y3 * qs);
+        }
+        a[it].x *= gt.x, a[it].y *= gt.y, a[it].z *= gt.z, a[it].w *= gt.w;
+    }
+    __syncwarp();          // everyone has read the fp32 tile; overwrite it with the final tile
+    if (p.store_mode == 1) {
+        uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            uint2 pk;
+            pk.x = pack_bf16(a[it].x, a[it].y);
+            pk.y = pack_bf16(a[it].z, a[it].w);
+            *reinterpret_cast<uint2*>(sb + r * 64 + q * 8) = pk;
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            *reinterpret_cast<float4*>(stage + r * 32 + q * 4) = a[it];
+        }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        if (p.store_mode == 2) tma_reduce_add_3d(&p.omap, stage, c0, t_base, b);
+        else tma_store_3d(&p.omap, stage, c0, t_base, b);
+        bulk_commit();
+    }
+}
+
 // Persistent, warp-specialised tcgen05 GEMM.  One CTA per SM walks output tiles
 // (n fastest, so CTAs running together share the A tile in L2); the accumulator is
 // double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.
-template <int BN, int STAGES>
+// EPI: 0 = register/LSU epilogue (any pattern), 1 = TMA-store epilogue, 2 = TMA-store epilogue with a
+// pair activation (items of 64 accumulator columns).  Separate instantiations keep each path's
+// registers and code small.
+template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
     using S = TcSmem<BN, STAGES>;
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
@@ -302,6 +438,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             tma_prefetch_desc(&p.amap[i]);
             tma_prefetch_desc(&p.wmap[i]);
         }
+        if (p.store_mode != 0) tma_prefetch_desc(&p.omap);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -398,6 +535,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         const int lg = warp & 3;             // TMEM lane group this warp may access
         float* stage_buf = reinterpret_cast<float*>(smem + S::EPI_OFFSET) + ew * 32 * kStageRowF;
         const uint32_t taddr = tmem_base + group * ACC_COLS + (static_cast<uint32_t>(lg * 32) << 16);
+        constexpr bool tma_mode = EPI != 0;
+        constexpr bool pair = EPI == 2;
+        constexpr int acc_per_item = EPI == 2 ? 64 : 32;   // accumulator columns per work item
         struct Item {
             int it, ch, b, t_base, n0c;
             bool valid, last;
@@ -415,26 +555,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 x.b = m_tile / p.tiles_per_batch;
                 x.t_base = (m_tile % p.tiles_per_batch) * BM + lg * 32;
                 const int n0 = n_tile * BN;
-                x.n0c = n0 + ch * 32;
-                x.last = (ch + 1) * 32 >= min(BN, p.epi.N - n0);
+                x.n0c = n0 + ch * acc_per_item;
+                x.last = (ch + 1) * acc_per_item >= min(BN, p.epi.N - n0);
             }
             return x;
         };
+        // geometry used by the prefetch (4 columns per lane, 8 steps) in TMA mode
+        EpiChunk g_tma;
+        g_tma.co = 32, g_tma.lanes_per_row = 8, g_tma.rows_per_it = 4, g_tma.n_it = 8, g_tma.vec = true;
         Item cur = make_item(group, 0);
         EpiChunk g_cur = epi_chunk_geom(p.epi, cur.n0c);
+        if constexpr (tma_mode) { g_cur = g_tma; g_cur.c0 = pair ? (cur.n0c >> 1) : cur.n0c; }
         float4 rr_cur[8], rr_nxt[8];
-        if (cur.valid && g_cur.vec && cur.t_base < p.T)
+        const bool want_prefetch = !tma_mode || p.epi.act == SVC_ACT_ROPE;
+        if (cur.valid && want_prefetch && g_cur.vec && cur.t_base < p.T)
             epi_prefetch(p.epi, g_cur, lane, cur.b, cur.t_base, p.T, rr_cur);
         while (cur.valid) {
             if (cur.ch == 0) {
                 mbar_wait(&tmem_full_bar[group], (cur.it >> 1) & 1);
                 tc_fence_after();
             }
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + cur.ch * 32, r);
+            uint32_t r[32], r2[EPI == 2 ? 32 : 1];
+            tmem_ld_32x32(taddr + cur.ch * acc_per_item, r);
+            if constexpr (EPI == 2) tmem_ld_32x32(taddr + cur.ch * 64 + 32, r2);
             const Item nxt = cur.last ? make_item(cur.it + 2, 0) : make_item(cur.it, cur.ch + 1);
-            const EpiChunk g_nxt = epi_chunk_geom(p.epi, nxt.n0c);
-            if (nxt.valid && g_nxt.vec && nxt.t_base < p.T)
+            EpiChunk g_nxt = epi_chunk_geom(p.epi, nxt.n0c);
+            if constexpr (tma_mode) { g_nxt = g_tma; g_nxt.c0 = pair ? (nxt.n0c >> 1) : nxt.n0c; }
+            if (nxt.valid && want_prefetch && g_nxt.vec && nxt.t_base < p.T)
                 epi_prefetch(p.epi, g_nxt, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
             tc_wait_ld();
             if (cur.last) {                     // this warp has read its whole slice of the buffer
@@ -442,17 +589,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
             }
-            float v[32];
+            if (cur.t_base < p.T && !(p.dbg & 1)) {
+                if constexpr (EPI == 0) {
+                    float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (cur.t_base < p.T && !(p.dbg & 1))
-                epilogue_chunk_coalesced(p.epi, g_cur, stage_buf, lane, cur.b, cur.t_base, p.T, cur.n0c,
-                                         v, rr_cur, p.dbg);
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    epilogue_chunk_coalesced(p.epi, g_cur, stage_buf, lane, cur.b, cur.t_base, p.T,
+                                             cur.n0c, v, rr_cur, p.dbg);
+                } else if constexpr (EPI == 2) {
+                    float v[64];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]), v[32 + j] = __uint_as_float(r2[j]);
+                    epilogue_item_tma<true>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                } else {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    epilogue_item_tma<false>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                }
+            }
             cur = nxt;
             g_cur = g_nxt;
 #pragma unroll
             for (int i = 0; i < 8; ++i) rr_cur[i] = rr_nxt[i];
         }
+        if (tma_mode && lane == 0) bulk_wait_read0();   // smem must outlive the last bulk store
     }
     tc_fence_before();
     __syncthreads();
@@ -580,20 +741,51 @@ bool encode_bf16_map(CUtensorMap* map, const void* ptr, int K, long long rows, l
     return r == CUDA_SUCCESS;
 }
 
-template <int BN, int STAGES>
-static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
+// (N_out, T, B) view of an output tensor for the TMA-store epilogue: box {32, 32, 1}, no swizzle
+static bool encode_out_map(CUtensorMap* map, const void* ptr, bool f32, int n_out, long long rows,
+                           long long rstride, long long batches, long long bstride) {
+    EncodeTiledFn fn = get_encode_fn();
+    const int es = f32 ? 4 : 2;
+    if (fn == nullptr || ptr == nullptr) return false;
+    if (reinterpret_cast<uintptr_t>(ptr) % 16 != 0 || (rstride * es) % 16 != 0) return false;
+    if (batches > 1 && (bstride * es) % 16 != 0) return false;
+    if (batches <= 1) bstride = rows * rstride;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(n_out), static_cast<cuuint64_t>(rows),
+                          static_cast<cuuint64_t>(batches)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(rstride * es), static_cast<cuuint64_t>(bstride * es)};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES, int EPI>
+static int launch_tc_epi(const TcParams& p, int m_tiles, cudaStream_t stream) {
     using S = TcSmem<BN, STAGES>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             S::TOTAL);
+        cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         attr_set = true;
     }
     const int tiles = m_tiles * p.n_tiles;
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    gemm_tc_kernel<BN, STAGES><<<grid, kTcThreads, S::TOTAL, stream>>>(p);
+    gemm_tc_kernel<BN, STAGES, EPI><<<grid, kTcThreads, S::TOTAL, stream>>>(p);
     SVC_CHECK_LAUNCH();
     return SVC_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
+    const bool pair = p.epi.act == SVC_ACT_SWIGLU_PAIR || p.epi.act == SVC_ACT_TANH_SIG_PAIR;
+    if (p.store_mode == 0) return launch_tc_epi<BN, STAGES, 0>(p, m_tiles, stream);
+    if constexpr (BN >= 64) {
+        if (pair) return launch_tc_epi<BN, STAGES, 2>(p, m_tiles, stream);
+    }
+    return launch_tc_epi<BN, STAGES, 1>(p, m_tiles, stream);
 }
 
 static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
@@ -665,6 +857,25 @@ static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
     p.tiles_per_batch = (d.T + BM - 1) / BM;
     p.n_tiles = (d.N + BN - 1) / BN;
     p.epi = make_epi_params(d);
+    // ---- TMA-store epilogue when the output pattern allows it ------------------------------
+    static const int no_tma_store = getenv("SVC_NO_TMA_STORE") ? 1 : 0;
+    p.store_mode = 0;
+    if (p.epi.vec_ok && !no_tma_store) {
+        const bool res_inplace = d.res != nullptr && d.res == d.out_f32 && d.res_bstride == d.of_bstride &&
+                                 d.res_rstride == d.of_rstride;
+        if (d.out_op != nullptr && d.out_f32 == nullptr && d.res == nullptr && !d.accumulate) {
+            if (encode_out_map(&p.omap, d.out_op, false, p.epi.N_out, d.T, d.oo_rstride, d.B, d.oo_bstride))
+                p.store_mode = 1;
+        } else if (d.out_f32 != nullptr && d.out_op == nullptr && d.act != SVC_ACT_ROPE) {
+            const bool add = (res_inplace && !d.accumulate && d.alpha == 1.0f) ||
+                             (d.res == nullptr && d.accumulate);
+            const bool plain = d.res == nullptr && !d.accumulate;
+            if ((add || plain) &&
+                encode_out_map(&p.omap, d.out_f32, true, p.epi.N_out, d.T, d.of_rstride, d.B, d.of_bstride))
+                p.store_mode = add ? 2 : 3;
+        }
+    }
+    if (BN < 64 && (d.act == SVC_ACT_SWIGLU_PAIR || d.act == SVC_ACT_TANH_SIG_PAIR)) p.store_mode = 0;
     const int m_tiles = d.B * p.tiles_per_batch;
     switch (BN) {
         case 32: return launch_tc<32, 8>(p, m_tiles, stream);
