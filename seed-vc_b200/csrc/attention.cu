@@ -10,6 +10,8 @@
 //   warps 2-5: one query row per thread: online softmax on S_j (tcgen05.ld), P_j -> bf16 ->
 //             128B-swizzled smem for the PV MMA, running O in registers rescaled per block.
 // fp32: FFMA kernel, one query per thread ("fp32 mode").
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace svc {
@@ -19,7 +21,7 @@ constexpr int AT_QT = 2;     // Q tiles per CTA (ping-pong between two softmax g
 constexpr int AT_BN = 128;   // keys per block
 constexpr int AT_HD = 64;
 constexpr int AT_KST = 3;    // K / V ring depth
-constexpr int AT_THREADS = 64 + AT_QT * 128;
+constexpr int AT_THREADS = 128 + AT_QT * 128;   // warpgroup 0: TMA, MMA, 2 idle warps; WG 1-2: softmax
 
 struct alignas(64) AttnTcParams {
     CUtensorMap qmap, kmap, vmap;  // (H*64, T, B) bf16 views, box {64, 128, 1}
@@ -48,6 +50,15 @@ __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // 32 lanes x 32 columns store (thread i writes row lane_base + i)
@@ -129,7 +140,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     const uint32_t tmem_S = tmem_base;                    // AT_QT x 128 columns
     const uint32_t tmem_O = tmem_base + AT_QT * AT_BN;    // AT_QT x 64 columns
 
+    // warpgroup 0 (TMA, MMA, two idle warps) hands its registers to the two softmax warpgroups
     if (warp == 0) {
+        reg_dealloc<40>();
         if (lane == 0) {
             mbar_expect_tx(q_full, AT_QT * S::TILE);
             for (int g = 0; g < AT_QT; ++g)
@@ -148,6 +161,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             }
         }
     } else if (warp == 1) {
+        reg_dealloc<40>();
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
             const uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_HD, 0, 1);   // B (=V) MN-major
@@ -190,9 +204,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 }
             }
         }
+    } else if (warp < 4) {
+        reg_dealloc<40>();
     } else {
         // ===================== softmax groups: one query row per thread =====================
-        const int g = (warp - 2) >> 2;
+        reg_alloc<224>();
+        const int g = (warp - 4) >> 2;
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
@@ -203,28 +220,38 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         uint8_t* pbuf = smem + S::P_OFF + g * 2 * S::TILE + row * 128;
         float m_ref = 0.f, l_run = 0.f;       // m_ref in log2 units (already * log2e)
 
-        for (int j = 0; j < n_blocks; ++j) {
+        // one KV block of this row; TAIL = the block holds keys >= kv_len (masked), only the last one
+        auto block = [&](int j, auto tail_tag) {
+            constexpr bool TAIL = decltype(tail_tag)::value;
             mbar_wait(&s_full[g], j & 1);
             tc_fence_after();
-            uint32_t s[4][32];
+            float s[4][32];
+            {
+                uint32_t r[4][32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, s[c]);
-            tc_wait_ld();
-            tc_fence_before();
-            mbar_arrive(&s_empty[g]);
-            const int kbase = j * AT_BN;
-            if (kbase + AT_BN > kv_len) {     // only the last block has masked keys
+                for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, r[c]);
+                tc_wait_ld();
+                tc_fence_before();
+                mbar_arrive(&s_empty[g]);
+                const int kbase = j * AT_BN;
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (kbase + c * 32 + i >= kv_len) s[c][i] = 0xff800000u;   // -inf
+                    for (int i = 0; i < 32; ++i) {
+                        s[c][i] = __uint_as_float(r[c][i]);
+                        if (TAIL && kbase + c * 32 + i >= kv_len) s[c][i] = -INFINITY;
+                    }
             }
-            float mx = -INFINITY;
+            // row max with 8 independent chains (a single fmax chain is 128 x 4 cycles of latency)
+            float mxa[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mxa[i] = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
+                for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], s[c][i]);
+            float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
             mx *= kLog2e;
             bool need = false;
             float m_new = m_ref;
@@ -234,17 +261,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 need = true;
                 m_new = mx;
             }
-            float l_blk = 0.f;
+            float la[4] = {0.f, 0.f, 0.f, 0.f};     // independent partial sums
             uint32_t pk[64];
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(s[c][i]), kLog2e, -m_new));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(s[c][i + 1]), kLog2e, -m_new));
-                    l_blk += p0 + p1;
+                    const float p0 = fast_exp2(fmaf(s[c][i], kLog2e, -m_new));
+                    const float p1 = fast_exp2(fmaf(s[c][i + 1], kLog2e, -m_new));
+                    la[(i >> 1) & 3] += p0 + p1;
                     pk[c * 16 + (i >> 1)] = pack_bf16(p0, p1);
                 }
+            const float l_blk = (la[0] + la[1]) + (la[2] + la[3]);
             // PV of the previous block must have retired before P / O are touched
             mbar_wait(&p_empty[g], (j & 1) ^ 1);
             if (__any_sync(0xffffffffu, need)) {
@@ -274,7 +302,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[g]);
-        }
+        };
+        for (int j = 0; j < n_blocks - 1; ++j) block(j, std::false_type{});
+        if (n_blocks * AT_BN > kv_len) block(n_blocks - 1, std::true_type{});
+        else block(n_blocks - 1, std::false_type{});
         // last PV retired -> O complete
         mbar_wait(&p_empty[g], (n_blocks - 1) & 1);
         tc_fence_after();
