@@ -196,12 +196,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 if (g == AT_QT - 1) tc_commit(&v_empty[st]);
             };
             mbar_wait(q_full, 0);
+            // S_g(j+1) only needs softmax g to have pulled S_g(j) into registers (early in its
+            // block), so it is issued BEFORE the PV of block j.
             for (int g = 0; g < AT_QT; ++g) issue_s(g, 0);
             for (int j = 0; j < n_blocks; ++j) {
-                for (int g = 0; g < AT_QT; ++g) {
-                    issue_pv(g, j);
-                    if (j + 1 < n_blocks) issue_s(g, j + 1);
-                }
+                if (j + 1 < n_blocks)
+                    for (int g = 0; g < AT_QT; ++g) issue_s(g, j + 1);
+                for (int g = 0; g < AT_QT; ++g) issue_pv(g, j);
             }
         }
     } else if (warp < 4) {
