@@ -37,6 +37,17 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_trace() -> str:
+    """Debug variant with -DSVC_TRACE (clock64 event stamps); separate .so, never used by the product."""
+    out = os.path.join(PKG, "libseedvc_b200_trace.so")
+    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-DSVC_TRACE", "-shared", "-o", out] + \
+        [os.path.join(CSRC, s) for s in SOURCES] + ["-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "seedvc_b200.h"))
@@ -68,4 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--trace" in sys.argv:
+        print(build_trace())
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -70,7 +70,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("SEEDVC_B200_LIB") or LIB_PATH
     if not os.path.exists(p):
         raise SvcError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -10,11 +10,23 @@
 //   warps 2-5: one query row per thread: online softmax on S_j (tcgen05.ld), P_j -> bf16 ->
 //             128B-swizzled smem for the PV MMA, running O in registers rescaled per block.
 // fp32: FFMA kernel, one query per thread ("fp32 mode").
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
 
 namespace svc {
+
+#ifdef SVC_TRACE
+__device__ long long g_attn_trace[4][64][8];   // [role][block][event] clock64 stamps of CTA (0,0,0)
+#define TRACE(role, j, ev)                                                                   \
+    do {                                                                                     \
+        if (trace_on && (j) < 64) g_attn_trace[role][j][ev] = clock64();                     \
+    } while (0)
+#else
+#define TRACE(role, j, ev) do {} while (0)
+#endif
 
 constexpr int AT_BM = 128;   // queries per Q tile (one TMEM lane each)
 constexpr int AT_QT = 2;     // Q tiles per CTA (ping-pong between two softmax groups)
@@ -29,6 +41,7 @@ struct alignas(64) AttnTcParams {
     long long o_bstride, o_rstride;
     const int* kv_len;
     int T, H;
+    int dbg;   // SVC_DBG_ATTN: 1 = issue 1 of 8 PV MMAs, 2 = issue 1 of 4 QK^T MMAs (timing experiments)
 };
 
 struct AttnSmem {
@@ -109,6 +122,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     int kv_len = p.kv_len != nullptr ? p.kv_len[b] : p.T;
     kv_len = max(1, min(kv_len, p.T));
     const int n_blocks = (kv_len + AT_BN - 1) / AT_BN;
+#ifdef SVC_TRACE
+    const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
+                          (warp == 1 || warp == 4);
+#endif
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.qmap);
@@ -117,9 +134,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         mbar_init(q_full, 1);
         for (int i = 0; i < AT_KST; ++i) {
             mbar_init(&k_full[i], 1);
-            mbar_init(&k_empty[i], 1);
+            mbar_init(&k_empty[i], AT_QT);
             mbar_init(&v_full[i], 1);
-            mbar_init(&v_empty[i], 1);
+            mbar_init(&v_empty[i], AT_QT);
         }
         for (int i = 0; i < AT_QT; ++i) {
             mbar_init(&s_full[i], 1);
@@ -151,58 +168,92 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 const int st = j % AT_KST;
                 const uint32_t ph = (j / AT_KST) & 1;
                 mbar_wait(&k_empty[st], ph ^ 1);
+#ifdef SVC_TRACE
+                if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) g_attn_trace[0][j][3] = clock64();
+#endif
                 mbar_expect_tx(&k_full[st], S::TILE);
                 tma_load_3d(smem + S::K_OFF + st * S::TILE, &p.kmap, &k_full[st], h * AT_HD,
                             j * AT_BN, b);
                 mbar_wait(&v_empty[st], ph ^ 1);
+#ifdef SVC_TRACE
+                if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) g_attn_trace[0][j][4] = clock64();
+#endif
                 mbar_expect_tx(&v_full[st], S::TILE);
                 tma_load_3d(smem + S::V_OFF + st * S::TILE, &p.vmap, &v_full[st], h * AT_HD,
                             j * AT_BN, b);
+#ifdef SVC_TRACE
+                if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) {
+                    while (!mbar_test_wait(&k_full[st], ph)) {}
+                    g_attn_trace[2][j][0] = clock64();      // K_j landed (producer view)
+                    while (!mbar_test_wait(&v_full[st], ph)) {}
+                    g_attn_trace[2][j][1] = clock64();      // V_j landed
+                }
+#endif
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 2) {
         reg_dealloc<40>();
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
             const uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_HD, 0, 1);   // B (=V) MN-major
+            // descriptor lo words of the smem regions (address field only varies)
+            const uint32_t q_lo0 = desc_lo(smem_u32(smem + S::Q_OFF));
+            const uint32_t k_lo0 = desc_lo(smem_u32(smem + S::K_OFF));
+            const uint32_t p_lo0 = desc_lo(smem_u32(smem + S::P_OFF));
+            const uint32_t v_lo0 = desc_lo(smem_u32(smem + S::V_OFF), 1024);   // MN-major: LBO = 1024
             auto issue_s = [&](int g, int j) {
                 const int st = j % AT_KST;
-                mbar_wait(&k_full[st], (j / AT_KST) & 1);
-                mbar_wait(&s_empty[g], (j & 1) ^ 1);          // softmax g has read S_g(j-1)
+                if (g == 0) TRACE(0, j, 2);
+                if (g == 1) TRACE(3, j, 3);
                 tc_fence_after();
-                const uint32_t sq = smem_u32(smem + S::Q_OFF + g * S::TILE);
-                const uint32_t sk = smem_u32(smem + S::K_OFF + st * S::TILE);
+                const uint32_t qlo = q_lo0 + g * (S::TILE >> 4);
+                const uint32_t klo = k_lo0 + st * (S::TILE >> 4);
 #pragma unroll
                 for (int k = 0; k < AT_HD / 16; ++k)
-                    tc_mma_f16(tmem_S + g * AT_BN, umma_desc_sw128(sq + k * 32, 0, 1024),
-                               umma_desc_sw128(sk + k * 32, 0, 1024), idesc_s, k != 0);
+                    tc_mma_f16_lh(tmem_S + g * AT_BN, qlo + k * 2, kDescHiSw128, klo + k * 2, kDescHiSw128,
+                                  idesc_s, k != 0);
                 tc_commit(&s_full[g]);
-                if (g == AT_QT - 1) tc_commit(&k_empty[st]);
+                if (g == 1) TRACE(3, j, 4);
             };
             auto issue_pv = [&](int g, int j) {
                 const int st = j % AT_KST;
-                mbar_wait(&v_full[st], (j / AT_KST) & 1);
-                mbar_wait(&p_full[g], j & 1);
+                if (g == 0) TRACE(0, j, 5);
+                if (g == 1) TRACE(3, j, 0);
                 tc_fence_after();
-                const uint32_t sp = smem_u32(smem + S::P_OFF + g * 2 * S::TILE);
-                const uint32_t sv = smem_u32(smem + S::V_OFF + st * S::TILE);
+                if (g == 1) TRACE(3, j, 1);
+                const uint32_t plo = p_lo0 + g * (2 * S::TILE >> 4);
+                const uint32_t vlo = v_lo0 + st * (S::TILE >> 4);
 #pragma unroll
-                for (int k = 0; k < AT_BN / 16; ++k) {
-                    const uint64_t da = umma_desc_sw128(sp + (k >> 2) * S::TILE + (k & 3) * 32, 0, 1024);
-                    const uint64_t db = umma_desc_mn_sw128(sv + k * 2048);
-                    tc_mma_f16(tmem_O + g * AT_HD, da, db, idesc_o, (j | k) != 0);
-                }
+                for (int k = 0; k < AT_BN / 16; ++k)
+                    tc_mma_f16_lh(tmem_O + g * AT_HD, plo + (k >> 2) * (S::TILE >> 4) + (k & 3) * 2,
+                                  kDescHiSw128, vlo + k * (2048 >> 4), kDescHiSw128, idesc_o,
+                                  (j | k) != 0);
+                if (g == 1) TRACE(3, j, 2);
                 tc_commit(&p_empty[g]);
-                if (g == AT_QT - 1) tc_commit(&v_empty[st]);
+                if (g == AT_QT - 1) TRACE(0, j, 6);
             };
             mbar_wait(q_full, 0);
-            // S_g(j+1) only needs softmax g to have pulled S_g(j) into registers (early in its
-            // block), so it is issued BEFORE the PV of block j.
-            for (int g = 0; g < AT_QT; ++g) issue_s(g, 0);
+            // One issuing thread per softmax group (warp 1 -> group 0, warp 2 -> group 1): the
+            // groups run independent S / PV chains, so neither waits behind the other's barriers
+            // or its ~75-cycle-per-MMA issue time.  K / V stages are released when both have
+            // committed (k_empty / v_empty count 2).
+            const int g = warp - 1;
+            mbar_wait(&k_full[0], 0);
+            issue_s(g, 0);
+            tc_commit(&k_empty[0]);
             for (int j = 0; j < n_blocks; ++j) {
-                if (j + 1 < n_blocks)
-                    for (int g = 0; g < AT_QT; ++g) issue_s(g, j + 1);
-                for (int g = 0; g < AT_QT; ++g) issue_pv(g, j);
+                if (j + 1 < n_blocks) {
+                    const int st = (j + 1) % AT_KST;
+                    mbar_wait(&k_full[st], ((j + 1) / AT_KST) & 1);
+                    mbar_wait(&s_empty[g], ((j + 1) & 1) ^ 1);      // softmax g has S_g(j) in registers
+                    issue_s(g, j + 1);
+                    tc_commit(&k_empty[st]);
+                }
+                const int st = j % AT_KST;
+                mbar_wait(&v_full[st], (j / AT_KST) & 1);
+                mbar_wait(&p_full[g], j & 1);
+                issue_pv(g, j);
+                tc_commit(&v_empty[st]);
             }
         }
     } else if (warp < 4) {
@@ -224,7 +275,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         // one KV block of this row; TAIL = the block holds keys >= kv_len (masked), only the last one
         auto block = [&](int j, auto tail_tag) {
             constexpr bool TAIL = decltype(tail_tag)::value;
+            TRACE(1, j, 0);
             mbar_wait(&s_full[g], j & 1);
+            TRACE(1, j, 1);
             tc_fence_after();
             float s[4][32];
             {
@@ -232,6 +285,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
                 for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, r[c]);
                 tc_wait_ld();
+                TRACE(1, j, 2);
+#ifdef SVC_TRACE
+                if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j < 64 && warp >= 6)
+                    g_attn_trace[2][j][warp - 4] = clock64();     // S load done, per softmax warp
+#endif
                 tc_fence_before();
                 mbar_arrive(&s_empty[g]);
                 const int kbase = j * AT_BN;
@@ -274,8 +332,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                     pk[c * 16 + (i >> 1)] = pack_bf16(p0, p1);
                 }
             const float l_blk = (la[0] + la[1]) + (la[2] + la[3]);
+            TRACE(1, j, 3);
             // PV of the previous block must have retired before P / O are touched
             mbar_wait(&p_empty[g], (j & 1) ^ 1);
+            TRACE(1, j, 4);
             if (__any_sync(0xffffffffu, need)) {
                 tc_fence_after();
                 const float alpha = need ? fast_exp2(m_ref - m_new) : 1.0f;
@@ -300,9 +360,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 *reinterpret_cast<uint4*>(tile + (((q & 7) ^ (row & 7)) << 4)) =
                     make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
             }
+            TRACE(1, j, 5);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[g]);
+            TRACE(1, j, 6);
         };
         for (int j = 0; j < n_blocks - 1; ++j) block(j, std::false_type{});
         if (n_blocks * AT_BN > kv_len) block(n_blocks - 1, std::true_type{});
@@ -434,6 +496,8 @@ extern "C" int svc_attention(const void* q, const void* k, const void* v, long l
         p.kv_len = kv_len;
         p.T = T;
         p.H = H;
+        static const int dbg = getenv("SVC_DBG_ATTN") ? atoi(getenv("SVC_DBG_ATTN")) : 0;
+        p.dbg = dbg;
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -458,3 +522,10 @@ extern "C" int svc_attention(const void* q, const void* k, const void* v, long l
     SVC_CHECK_LAUNCH();
     return SVC_OK;
 }
+
+#ifdef SVC_TRACE
+extern "C" int svc_debug_attn_trace(long long* host, int n) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host, svc::g_attn_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
+#endif

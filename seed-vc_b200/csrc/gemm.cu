@@ -493,6 +493,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            const uint32_t a_lo0 = desc_lo(smem_u32(smem));
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int n0 = (tile % p.n_tiles) * BN;
                 int n_umma = p.epi.N - n0;
@@ -505,15 +506,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 for (int kb = 0; kb < p.total_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-                    const uint32_t sb = sa + S::A_BYTES;
+                    const uint32_t alo = a_lo0 + stage * (S::STAGE_BYTES >> 4);
+                    const uint32_t blo = alo + (S::A_BYTES >> 4);
                     if (!(p.dbg & 2)) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint64_t da = umma_desc_sw128(sa + k * 32, 0, 1024);
-                            const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
-                            tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                        }
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc_mma_f16_lh(d_tmem, alo + k * 2, kDescHiSw128, blo + k * 2, kDescHiSw128,
+                                          idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) {

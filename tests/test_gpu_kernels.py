@@ -43,9 +43,13 @@ def run_gemm_case(mode, simt, B, T, N, Ks, shifts=None, rows=None, bias=False, r
     shifts = shifts or [0] * len(Ks)
     rows = rows or T
     segs, segs_ref = [], []
+    # conv-style cases: one activation view and one (taps, N, K) weight tensor, like the engine
+    w_all = rnd(len(Ks), N, Ks[0], seed=seed + 1, scale=1 / math.sqrt(Ks[0] * len(Ks)), dtype=od) \
+        if share_a else None
     for i, K in enumerate(Ks):
         A = segs[0][0] if (share_a and i > 0) else rnd(B, rows, K, seed=seed + 10 * i, dtype=od)
-        W = rnd(N, K, seed=seed + 10 * i + 1, scale=1 / math.sqrt(K * len(Ks)), dtype=od)
+        W = w_all[i] if share_a else rnd(N, K, seed=seed + 10 * i + 1,
+                                         scale=1 / math.sqrt(K * len(Ks)), dtype=od)
         segs.append((A, shifts[i], W))
         segs_ref.append((A.float(), shifts[i], W.float()))
     pair = act in (2, 3)
