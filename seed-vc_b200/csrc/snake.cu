@@ -128,6 +128,128 @@ __global__ void __launch_bounds__(256) snake_aa_kernel(const TI* __restrict__ x,
     }
 }
 
+// v2: two adjacent channels per thread with packed fp32x2 arithmetic (FFMA2 halves the FIR
+// instruction count), float4 / 8-byte global accesses.  Same maths and tiling idea as above.
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+template <bool PRECISE>
+__device__ __forceinline__ float2 snake_fn2(float2 u, float2 a, float2 inv_b) {
+    const float sx = PRECISE ? sinf(u.x * a.x) : __sinf(u.x * a.x);
+    const float sy = PRECISE ? sinf(u.y * a.y) : __sinf(u.y * a.y);
+    return make_float2(fmaf(inv_b.x * sx, sx, u.x), fmaf(inv_b.y * sy, sy, u.y));
+}
+
+template <typename TI>
+__device__ __forceinline__ float4 load4(const TI* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
+    const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+    return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+
+template <typename TI, typename TO, int CT, int LPT, bool PRECISE>
+__global__ void __launch_bounds__(256) snake_aa2_kernel(const TI* __restrict__ x, TO* __restrict__ out,
+                                                        const float* __restrict__ a_p,
+                                                        const float* __restrict__ invb_p, int L, int C) {
+    constexpr int LANES = CT / 2;
+    constexpr int NCHUNK = 256 / LANES;
+    constexpr int TL = NCHUNK * LPT;
+    constexpr int ROWS = TL + 10;
+    constexpr int STRIDE = CT + 2;          // even (float2 alignment), spreads chunks over banks
+    extern __shared__ float xs2[];
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CT;
+    const int l0 = blockIdx.x * TL;
+    const TI* xb = x + static_cast<long long>(b) * L * C;
+    constexpr int V4 = CT / 4;
+    for (int i = threadIdx.x; i < ROWS * V4; i += 256) {
+        const int r = i / V4, c4 = (i % V4) * 4;
+        const int l = min(max(l0 - 5 + r, 0), L - 1);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + c4 < C) v = load4<TI>(xb + static_cast<long long>(l) * C + c0 + c4);
+        float* d = xs2 + r * STRIDE + c4;
+        *reinterpret_cast<float2*>(d) = make_float2(v.x, v.y);
+        *reinterpret_cast<float2*>(d + 2) = make_float2(v.z, v.w);
+    }
+    __syncthreads();
+    const int lane2 = threadIdx.x % LANES;
+    const int chunk = threadIdx.x / LANES;
+    const int c = c0 + 2 * lane2;
+    if (chunk >= NCHUNK || c >= C) return;
+    const int n0 = l0 + chunk * LPT;
+    if (n0 >= L) return;
+    const float2 a = __ldg(reinterpret_cast<const float2*>(a_p + c));
+    const float2 inv_b = __ldg(reinterpret_cast<const float2*>(invb_p + c));
+    TO* ob = out + static_cast<long long>(b) * L * C + c;
+    const float* col = xs2 + 2 * lane2;
+    auto ld = [&](int row) { return *reinterpret_cast<const float2*>(col + row * STRIDE); };
+    auto st = [&](int n, float2 y) {
+        if constexpr (sizeof(TO) == 4) {
+            *reinterpret_cast<float2*>(ob + static_cast<long long>(n) * C) = y;
+        } else {
+            *reinterpret_cast<__nv_bfloat162*>(ob + static_cast<long long>(n) * C) = __floats2bfloat162_rn(y.x, y.y);
+        }
+    };
+    const int n_last = min(n0 + LPT, L) - 1;
+    const bool interior = (2 * n0 - 5 >= 0) && (2 * n_last + 6 <= 2 * L - 1) && (n_last == n0 + LPT - 1);
+    if (interior) {
+        float2 xw[6], uw[12];
+        const int r0 = n0 - l0 + 5;
+#pragma unroll
+        for (int pz = 0; pz < 5; ++pz) {
+            float2 e = splat2(0.f), o = splat2(0.f);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const float2 xv = ld(r0 + pz - j);
+                e = __ffma2_rn(splat2(c_h12[2 * j]), xv, e);
+                o = __ffma2_rn(splat2(c_h12[2 * j + 1]), xv, o);
+            }
+            uw[2 * pz] = snake_fn2<PRECISE>(__fmul2_rn(e, splat2(2.0f)), a, inv_b);
+            uw[2 * pz + 1] = snake_fn2<PRECISE>(__fmul2_rn(o, splat2(2.0f)), a, inv_b);
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) xw[j + 1] = ld(r0 + j);
+#pragma unroll
+        for (int i = 0; i < LPT; ++i) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) xw[j] = xw[j + 1];
+            xw[5] = ld(r0 + i + 5);
+            float2 e = splat2(0.f), o = splat2(0.f);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                e = __ffma2_rn(splat2(c_h12[2 * j]), xw[5 - j], e);
+                o = __ffma2_rn(splat2(c_h12[2 * j + 1]), xw[5 - j], o);
+            }
+            uw[10] = snake_fn2<PRECISE>(__fmul2_rn(e, splat2(2.0f)), a, inv_b);
+            uw[11] = snake_fn2<PRECISE>(__fmul2_rn(o, splat2(2.0f)), a, inv_b);
+            float2 y = splat2(0.f);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) y = __ffma2_rn(splat2(c_h12[k]), uw[k], y);
+            st(n0 + i, y);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) uw[k] = uw[k + 2];
+        }
+    } else {
+        for (int n = n0; n <= n_last; ++n) {
+            float y0 = 0.f, y1 = 0.f;
+            auto xat0 = [&](int l) { return col[(l - l0 + 5) * STRIDE]; };
+            auto xat1 = [&](int l) { return col[(l - l0 + 5) * STRIDE + 1]; };
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                y0 = fmaf(c_h12[k], up_point<PRECISE>(2 * n + k - 5, L, a.x, inv_b.x, xat0), y0);
+                y1 = fmaf(c_h12[k], up_point<PRECISE>(2 * n + k - 5, L, a.y, inv_b.y, xat1), y1);
+            }
+            st(n, make_float2(y0, y1));
+        }
+    }
+}
+
 // activation_post + conv_post (C -> 1, k taps, zero padding) + clamp / tanh.
 // Reference: modules/bigvgan/bigvgan.py:377-384.
 template <bool PRECISE>
@@ -177,12 +299,37 @@ __global__ void __launch_bounds__(256) snake_conv_post_kernel(
     }
 }
 
+template <typename TI, typename TO, int CT, int LPT, bool PRECISE>
+static void launch_snake2(const TI* xi, TO* o, const float* a, const float* inv_b, int B, int L, int C,
+                          cudaStream_t st) {
+    constexpr int LANES = CT / 2, NCHUNK = 256 / LANES, TL = NCHUNK * LPT;
+    constexpr int SMEM = (TL + 10) * (CT + 2) * 4;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(snake_aa2_kernel<TI, TO, CT, LPT, PRECISE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        attr = true;
+    }
+    dim3 grid((L + TL - 1) / TL, (C + CT - 1) / CT, B);
+    snake_aa2_kernel<TI, TO, CT, LPT, PRECISE><<<grid, 256, SMEM, st>>>(xi, o, a, inv_b, L, C);
+}
+
 template <typename TI, typename TO, bool PRECISE>
 static int launch_snake(const void* x, void* out, const float* a, const float* inv_b, int B, int L,
                         int C, cudaStream_t st) {
     const TI* xi = static_cast<const TI*>(x);
     TO* o = static_cast<TO*>(out);
-    if (C % 32 == 0 || C > 64) {
+    const bool al = reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0 &&
+                    reinterpret_cast<uintptr_t>(a) % 8 == 0 && reinterpret_cast<uintptr_t>(inv_b) % 8 == 0;
+    if (al && C % 64 == 0) {
+        launch_snake2<TI, TO, 64, 16, PRECISE>(xi, o, a, inv_b, B, L, C, st);
+    } else if (al && C % 32 == 0) {
+        launch_snake2<TI, TO, 32, 16, PRECISE>(xi, o, a, inv_b, B, L, C, st);
+    } else if (al && C % 48 == 0) {
+        launch_snake2<TI, TO, 48, 16, PRECISE>(xi, o, a, inv_b, B, L, C, st);
+    } else if (al && C % 24 == 0) {
+        launch_snake2<TI, TO, 24, 16, PRECISE>(xi, o, a, inv_b, B, L, C, st);
+    } else if (C % 32 == 0 || C > 64) {
         constexpr int CT = 32, LPT = 16, TL = (256 / CT) * LPT;
         dim3 grid((L + TL - 1) / TL, (C + CT - 1) / CT, B);
         snake_aa_kernel<TI, TO, CT, LPT, PRECISE><<<grid, 256, 0, st>>>(xi, o, a, inv_b, L, C);
