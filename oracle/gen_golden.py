@@ -49,7 +49,8 @@ V2_CASES = [
     ("v2_small_nocfg", 60, 20, 1, (0.0, 0.0), False),
     ("v2_small_random_voice", 60, 20, 1, (0.7, 0.7), True),
 ]
-BIGVGAN_CASES = [("bigvgan_22k_t12", "bigvgan_22k", 1, 12), ("bigvgan_22k_b2_t7", "bigvgan_22k", 2, 7)]
+BIGVGAN_CASES = [("bigvgan_22k_t12", "bigvgan_22k", 1, 12), ("bigvgan_22k_b2_t7", "bigvgan_22k", 2, 7),
+                 ("bigvgan_44k_t6", "bigvgan_44k", 1, 6)]
 
 
 def v1_args(model, scaled):

@@ -6,7 +6,7 @@ $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
 $CMD > gpurun_out/ncu_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 100 -c 4 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 100 -c 6 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm capture exit $?"
 $CMD > gpurun_out/ncu_plain3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:attention_tc_kernel -s 10 -c 2 -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_attn.log 2>&1

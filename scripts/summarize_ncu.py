@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Turn the ncu artefacts in gpurun_out/ into the tracked summaries under profiles/.
+usage: python scripts/summarize_ncu.py <round tag, e.g. r1>"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+PROF = os.path.join(ROOT, "profiles")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+os.makedirs(PROF, exist_ok=True)
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "l1tex__throughput.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__shared_mem_per_block_dynamic", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+]
+
+# ---- launch list -----------------------------------------------------------------------------
+path = os.path.join(OUT, "launches.csv")
+if os.path.exists(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "").strip()
+        name = re.sub(r"<.*", "", name)
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        ms = v / 1e6 if u in ("ns", "nsecond") else v / 1e3 if u in ("us", "usecond") else v
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += ms
+    tot = sum(a[1] for a in agg.values())
+    with open(os.path.join(PROF, f"{tag}_launch_list_summary.md"), "w") as f:
+        f.write(f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none)\n\n"
+                "Command: `python bench.py --workload profile --steps 1 --warmup 1 --no-cpu-baseline "
+                "--no-profile` (config-2 shapes: whisper-small DiT + BigVGAN-22k, B=8, T=2580, 2 Euler "
+                "steps per conversion).  Times under ncu are cold-cache and serialised: compare SHARES.\n"
+                "`at::*` rows are one-time weight preparation / input staging done by torch at setup.\n\n"
+                "| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{k}` | {a[0]} | {a[1]:.3f} | {a[1] / tot:.3f} |\n")
+        f.write(f"\nTotal {tot:.2f} ms over {sum(a[0] for a in agg.values())} launches.\n")
+    print("wrote launch list summary")
+
+# ---- full captures ---------------------------------------------------------------------------
+for rep in sorted(os.listdir(OUT)):
+    if not rep.endswith(".ncu-rep") or rep == "prof_k.ncu-rep":
+        continue
+    p = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"],
+                       capture_output=True, text=True)
+    rows = list(csv.reader(p.stdout.splitlines()))
+    if len(rows) < 3:
+        continue
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    with open(os.path.join(PROF, f"{tag}_{rep.replace('.ncu-rep', '')}_full.md"), "w") as f:
+        f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` - {rep}\n\n")
+        for r in rows[2:]:
+            f.write(f"## {r[idx['Kernel Name']][:140]}\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for k in KEYS:
+                if k in idx:
+                    f.write(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |\n")
+            rd, wr = r[idx["dram__bytes_read.sum"]], r[idx["dram__bytes_write.sum"]]
+            f.write(f"\ntraffic = dram read + write = {rd} + {wr} {units[idx['dram__bytes_read.sum']]}\n\n")
+    print("wrote", rep)

@@ -97,7 +97,9 @@ __device__ __forceinline__ EpiChunk epi_chunk_geom(const EpiParams& e, int n0) {
     g.lanes_per_row = g.co >> 2;
     g.rows_per_it = 32 / g.lanes_per_row;
     g.n_it = 32 / g.rows_per_it;
-    g.vec = e.vec_ok && (g.c0 + g.co <= e.N_out) && !(e.act == SVC_ACT_ROPE && e.res != nullptr);
+    // partial last chunk is fine as long as whole float4 column groups are valid (N_out % 4 == 0,
+    // implied by vec_ok's N_out % 8 == 0): lanes past N_out simply idle
+    g.vec = e.vec_ok && !(e.act == SVC_ACT_ROPE && e.res != nullptr);
     return g;
 }
 
@@ -108,6 +110,7 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& e, const EpiChunk&
                                              int t_base, int T, float4 (&rr)[8]) {
     const int c = g.c0 + (lane % g.lanes_per_row) * 4;
     const int rsub = lane / g.lanes_per_row;
+    if (c >= e.N_out) return;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int t = t_base + it * g.rows_per_it + rsub;
@@ -189,6 +192,7 @@ transpose:
     const int c = g.c0 + q * 4;
     if (dbg & 8) return;
     if (g.vec) {
+        if (c >= e.N_out) return;
         float4 gt = make_float4(e.alpha, e.alpha, e.alpha, e.alpha);
         const bool is_rope = e.act == SVC_ACT_ROPE;
         const bool rope = is_rope && c < e.rope_cols;

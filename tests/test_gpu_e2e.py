@@ -88,13 +88,14 @@ def test_v2_golden(name, mode):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-@pytest.mark.parametrize("name", ["bigvgan_22k_t12", "bigvgan_22k_b2_t7"])
+@pytest.mark.parametrize("name", ["bigvgan_22k_t12", "bigvgan_22k_b2_t7", "bigvgan_44k_t6"])
 def test_bigvgan_golden(name, mode):
     g = load_golden(name)
     m = g["meta"]
-    if "voc" not in _models:
-        _models["voc"] = BigVGAN(configs.bigvgan_h(m["config"])).to(DEV)
-    voc = _models["voc"]
+    key = "voc" if m["config"] == "bigvgan_22k" else "voc44"
+    if key not in _models:
+        _models[key] = BigVGAN(configs.bigvgan_h(m["config"])).to(DEV)
+    voc = _models[key]
     voc.set_mode(mode)
     mel = synth.synth_mel(m["B"], voc.h.num_mels, m["Tm"]).to(DEV)
     wav = voc(mel)

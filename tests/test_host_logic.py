@@ -88,7 +88,7 @@ def test_batched_equals_per_utterance():
         assert float(out[b, :, n:].abs().max()) == 0.0 if n < T else True
 
 
-@pytest.mark.parametrize("name", ["bigvgan_22k_t12", "bigvgan_22k_b2_t7"])
+@pytest.mark.parametrize("name", ["bigvgan_22k_t12", "bigvgan_22k_b2_t7", "bigvgan_44k_t6"])
 def test_bigvgan_host_logic(name):
     g = load_golden(name)
     m = g["meta"]

@@ -63,7 +63,7 @@ def test_v2_sampler_matches_reference(name, manifest):
     assert rel_l2(out, g["out"]) < TOL
 
 
-@pytest.mark.parametrize("name", ["bigvgan_22k_t12", "bigvgan_22k_b2_t7"])
+@pytest.mark.parametrize("name", ["bigvgan_22k_t12", "bigvgan_22k_b2_t7", "bigvgan_44k_t6"])
 def test_bigvgan_matches_reference(name, manifest):
     g = load_golden(name)
     m = g["meta"]
