@@ -59,6 +59,55 @@ def kaiser_sinc_filter12():
     return (f / f.sum()).view(1, 1, ks)
 
 
+def conv_plan(weight, bias, dilation, od, length_divisor_ok=True):
+    """Tap list and weights for a 'same' Conv1d as a segmented GEMM.
+
+    Narrow layers (C_out < 96) are regrouped by *time-to-depth*: f consecutive frames are read
+    as one row of f*C channels - the (B, L, C) buffer IS a (B, L/f, f*C) buffer - and the kernel
+    becomes a block-structured (f*C x f*C) weight per super-tap:
+        y[f*q + p_out] = sum_k w_k x[f*q + p_out + (k - half) d]
+                       = sum_{s'} W'[s'][p_out-block, p_in-block] x'[q + s'],  m = p_out + (k-half) d,
+                         s' = floor(m / f), p_in = m - f s'.
+    Tiles get f x wider (N = f*C fills the 128-row MMA), their number drops f x, and for d = 1 the
+    k taps collapse into ~k/f super-taps.  Zero padding is unchanged (rows outside [0, L/f)).
+    Chosen only when it lowers the number of 64-wide K blocks issued per output frame.
+    Returns dict(f, shifts, w (n_taps, f*O, f*I) operand dtype, b (f*O,) fp32).
+    """
+    O, I, k = weight.shape
+    half = (k - 1) // 2
+    w = weight.detach().float()
+    b = bias.detach().float()
+    best = {"f": 1, "shifts": [(t - half) * dilation for t in range(k)],
+            "w": w.permute(2, 0, 1).contiguous().to(od), "b": b.contiguous(), "k": k}
+    if not length_divisor_ok or O != I or O >= 96:
+        return best
+    cost = {1: k * ((I + 63) // 64)}
+    cand = None
+    for f in (2, 4):
+        if O * f > 128:
+            continue
+        smin = min((p + (t - half) * dilation) // f for p in range(f) for t in range(k))
+        smax = max((p + (t - half) * dilation) // f for p in range(f) for t in range(k))
+        n_super = smax - smin + 1
+        if n_super > 16:
+            continue
+        c = n_super * ((f * I + 63) // 64) / f          # K blocks per original frame-tile
+        if c <= min(cost.values()):
+            cost[f] = c
+            cand = (f, smin, smax)
+    if cand is None:
+        return best
+    f, smin, smax = cand
+    wp = torch.zeros(smax - smin + 1, f * O, f * I, device=w.device)
+    for p_out in range(f):
+        for t in range(k):
+            m = p_out + (t - half) * dilation
+            sp, p_in = m // f, m % f
+            wp[sp - smin, p_out * O:(p_out + 1) * O, p_in * I:(p_in + 1) * I] += w[:, :, t]
+    return {"f": f, "shifts": list(range(smin, smax + 1)), "w": wp.to(od).contiguous(),
+            "b": b.repeat(f).contiguous(), "k": k}
+
+
 class BigVGAN(nn.Module):
     def __init__(self, h, use_cuda_kernel: bool = False, mode: str = "bf16"):
         super().__init__()
@@ -181,10 +230,9 @@ class BigVGAN(nn.Module):
                 pairs = []
                 for l, d in enumerate(h.resblock_dilation_sizes[j]):
                     pairs.append({
-                        "d": d, "k": ks,
                         "a1": snake(rb.activations[2 * l]), "a2": snake(rb.activations[2 * l + 1]),
-                        "w1": conv_w(rb.convs1[l]), "b1": f32(rb.convs1[l].bias),
-                        "w2": conv_w(rb.convs2[l]), "b2": f32(rb.convs2[l].bias),
+                        "c1": conv_plan(rb.convs1[l].weight, rb.convs1[l].bias, d, od),
+                        "c2": conv_plan(rb.convs2[l].weight, rb.convs2[l].bias, 1, od),
                     })
                 st["blocks"].append(pairs)
             stages.append(st)
@@ -226,20 +274,29 @@ class BigVGAN(nn.Module):
             for j, pairs in enumerate(st["blocks"]):
                 src = xs
                 for l, pr in enumerate(pairs):
-                    k, d = pr["k"], pr["d"]
-                    half = (k - 1) // 2
+                    c1, c2 = pr["c1"], pr["c2"]
+
+                    def segs_of(plan, a):
+                        f = plan["f"]
+                        av = a.view(B, L // f, O * f)
+                        return [(av, sh, plan["w"][i]) for i, sh in enumerate(plan["shifts"])], f
+
                     ops.snake(src, act, *pr["a1"])
-                    ops.gemm([(act, (t - half) * d, pr["w1"][t]) for t in range(k)], O, B=B, T=L,
-                             bias=pr["b1"], out_f32=xt)
+                    sg, f = segs_of(c1, act)
+                    fl = 2.0 * B * L * O * O            # algorithmic FLOPs per tap of the original conv
+                    ops.gemm(sg, O * f, B=B, T=L // f, bias=c1["b"], out_f32=xt.view(B, L // f, O * f),
+                             algo_flops=fl * c1["k"])
                     ops.snake(xt, act, *pr["a2"])
-                    segs = [(act, t - half, pr["w2"][t]) for t in range(k)]
+                    sg, f = segs_of(c2, act)
+                    vw = (B, L // f, O * f)
                     if l < len(pairs) - 1:
-                        ops.gemm(segs, O, B=B, T=L, bias=pr["b2"], res=src, out_f32=y)
+                        ops.gemm(sg, O * f, B=B, T=L // f, bias=c2["b"], res=src.view(vw), out_f32=y.view(vw),
+                                 algo_flops=fl * c2["k"])
                         src = y
                     else:   # last pair: residual, then (r0 + r1 + r2) / 3 accumulated in place
-                        ops.gemm(segs, O, B=B, T=L, bias=pr["b2"], res=src, alpha=1.0 / nk,
-                                 accumulate=j > 0, out_f32=nxt,
-                                 out_op=nxt_op if j == nk - 1 else None)
+                        ops.gemm(sg, O * f, B=B, T=L // f, bias=c2["b"], res=src.view(vw), alpha=1.0 / nk,
+                                 accumulate=j > 0, out_f32=nxt.view(vw), algo_flops=fl * c2["k"],
+                                 out_op=nxt_op.view(vw) if (j == nk - 1 and nxt_op is not None) else None)
             cur, cur_op = nxt, nxt_op
         out = torch.empty(B, L, dtype=f32, device=dev)
         ops.snake_conv_post(cur, *w["post_a"], w["post_w"], w["post_b"], out, self.use_tanh_at_final)

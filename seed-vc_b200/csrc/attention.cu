@@ -41,7 +41,7 @@ struct alignas(64) AttnTcParams {
     long long o_bstride, o_rstride;
     const int* kv_len;
     int T, H;
-    int dbg;   // SVC_DBG_ATTN: 1 = issue 1 of 8 PV MMAs, 2 = issue 1 of 4 QK^T MMAs (timing experiments)
+    int dbg;       // SVC_DBG_ATTN: 1 = issue 1 of 8 PV MMAs, 2 = issue 1 of 4 QK^T MMAs (timing experiments)
 };
 
 struct AttnSmem {

@@ -90,7 +90,8 @@ class Ops:
 
     # ------------------------------------------------------------------ GEMM
     def gemm(self, segs, N, *, B, T, bias=None, rowbias=None, act=ACT_NONE, rope=None, gate=None,
-             res=None, alpha=1.0, accumulate=False, out_f32=None, out_op=None, f32=False):
+             res=None, alpha=1.0, accumulate=False, out_f32=None, out_op=None, f32=False,
+             algo_flops=None):
         """out[b,t,:] = epilogue(sum_s A_s[b, t+shift_s, :] @ W_s.T); see svc_gemm.
 
         segs: [(A (B, rows, K), shift, W (N, K))]; rope: (table, rope_cols, pos0, q_cols, q_scale).
@@ -144,7 +145,8 @@ class Ops:
         ktot = sum(W.shape[1] for _, _, W in segs)
         cat = "gemm_f32" if (f32 or self.mode == "fp32") else ("gemm_tc" if self.backend == BACKEND_AUTO
                                                                else "gemm_simt")
-        self._t0(cat, 2.0 * B * T * N * ktot)
+        # algo_flops: algorithmic work when the launch computes a zero-padded regrouping
+        self._t0(cat, 2.0 * B * T * N * ktot if algo_flops is None else float(algo_flops))
         check(self.lib.svc_gemm(C.byref(d), self.backend, self._stream()), "svc_gemm")
         self._t1()
 

@@ -27,7 +27,8 @@ class EmuOps:
         return torch.zeros(*shape, dtype=dtype or torch.float32, device=device)
 
     def gemm(self, segs, N, *, B, T, bias=None, rowbias=None, act=ACT_NONE, rope=None, gate=None,
-             res=None, alpha=1.0, accumulate=False, out_f32=None, out_op=None, f32=False):
+             res=None, alpha=1.0, accumulate=False, out_f32=None, out_op=None, f32=False,
+             algo_flops=None):
         self.launches += 1
         dev = segs[0][0].device
         acc = torch.zeros(B, T, N, device=dev)
