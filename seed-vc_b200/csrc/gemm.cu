@@ -44,6 +44,16 @@ struct alignas(64) TcParams {
     EpiParams epi;
 };
 
+#ifdef SVC_TRACE
+__device__ long long g_gemm_trace[2][128][8];   // [0]: epilogue warp 2 lane 0 per item, [1]: MMA thread per tile
+#define GTRACE(role, idx, ev)                                                                       \
+    do {                                                                                            \
+        if (blockIdx.x == 0 && (idx) < 128) g_gemm_trace[role][idx][ev] = clock64();                \
+    } while (0)
+#else
+#define GTRACE(role, idx, ev) do {} while (0)
+#endif
+
 constexpr int kEpiWarps = 8;             // two epilogue groups of 4 warps (one per TMEM buffer)
 constexpr int kTcThreads = 64 + kEpiWarps * 32;    // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kStageRowF = 32;           // fp32 row of the per-warp transpose buffer (XOR-swizzled)
@@ -111,22 +121,29 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams& e, const EpiChunk&
     const int c = g.c0 + (lane % g.lanes_per_row) * 4;
     const int rsub = lane / g.lanes_per_row;
     if (c >= e.N_out) return;
+    // one base pointer + a constant row stride per step; rows past T are clamped (their values
+    // are never stored) so the loads need no per-row branches
+    const float* base;
+    long long rstride;
+    if (e.act == SVC_ACT_ROPE) {
+        if (c >= e.rope_cols) return;
+        base = e.rope_tab + static_cast<long long>(e.rope_pos0) * 64 + (c & 63);   // (cos, sin) x 2 pairs
+        rstride = 64;
+    } else if (e.res != nullptr) {
+        base = e.res + static_cast<long long>(b) * e.res_bstride + c;
+        rstride = e.res_rstride;
+    } else if (e.accumulate) {
+        base = e.out_f32 + static_cast<long long>(b) * e.of_bstride + c;
+        rstride = e.of_rstride;
+    } else {
+        return;
+    }
+    const int tmax = T - 1;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
-        const int t = t_base + it * g.rows_per_it + rsub;
-        if (it < g.n_it && t < T) {
-            if (e.act == SVC_ACT_ROPE) {
-                if (c < e.rope_cols)      // (cos, sin) of the two pairs this lane owns, coalesced
-                    rr[it] = __ldg(reinterpret_cast<const float4*>(
-                        e.rope_tab + static_cast<long long>(e.rope_pos0 + t) * 64 + (c & 63)));
-            } else if (e.res != nullptr)
-                rr[it] = __ldg(reinterpret_cast<const float4*>(
-                    e.res + static_cast<long long>(b) * e.res_bstride +
-                    static_cast<long long>(t) * e.res_rstride + c));
-            else if (e.accumulate)
-                rr[it] = *reinterpret_cast<const float4*>(
-                    e.out_f32 + static_cast<long long>(b) * e.of_bstride +
-                    static_cast<long long>(t) * e.of_rstride + c);
+        if (it < g.n_it) {
+            const int t = min(t_base + it * g.rows_per_it + rsub, tmax);
+            rr[it] = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(t) * rstride));
         }
     }
 }
@@ -504,7 +521,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 n_umma = n_umma > BN ? BN : ((n_umma + 15) & ~15);
                 const uint32_t idesc = umma_idesc_bf16(BM, n_umma, 0, 0);
                 const int acc = it & 1;
+                GTRACE(1, it, 0);
                 mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);   // epilogue drained this buffer
+                GTRACE(1, it, 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
                 for (int kb = 0; kb < p.total_kb; ++kb) {
@@ -525,6 +544,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     }
                 }
                 tc_commit(&tmem_full_bar[acc]);
+                GTRACE(1, it, 2);
             }
         }
     } else {
@@ -542,25 +562,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         constexpr bool pair = EPI == 2;
         constexpr int acc_per_item = EPI == 2 ? 64 : 32;   // accumulator columns per work item
         struct Item {
-            int it, ch, b, t_base, n0c;
+            int it, ch, b, t_base, n0c, ncols;
             bool valid, last;
         };
-        auto make_item = [&](int it, int ch) {
+        auto make_item = [&](int it, int ch) {          // full (re)computation: once per tile
             Item x;
             x.it = it;
             x.ch = ch;
             const int tile = blockIdx.x + it * gridDim.x;
             x.valid = tile < total_tiles;
-            x.b = 0, x.t_base = 0, x.n0c = 0, x.last = true;
+            x.b = 0, x.t_base = 0, x.n0c = 0, x.ncols = 0, x.last = true;
             if (x.valid) {
                 const int n_tile = tile % p.n_tiles;
                 const int m_tile = tile / p.n_tiles;
                 x.b = m_tile / p.tiles_per_batch;
-                x.t_base = (m_tile % p.tiles_per_batch) * BM + lg * 32;
+                x.t_base = (m_tile - x.b * p.tiles_per_batch) * BM + lg * 32;
                 const int n0 = n_tile * BN;
+                x.ncols = min(BN, p.epi.N - n0);
                 x.n0c = n0 + ch * acc_per_item;
-                x.last = (ch + 1) * acc_per_item >= min(BN, p.epi.N - n0);
+                x.last = (ch + 1) * acc_per_item >= x.ncols;
             }
+            return x;
+        };
+        auto next_item = [&](const Item& c) {           // within a tile: no divisions
+            if (c.last) return make_item(c.it + 2, 0);
+            Item x = c;
+            x.ch = c.ch + 1;
+            x.n0c = c.n0c + acc_per_item;
+            x.last = (x.ch + 1) * acc_per_item >= c.ncols;
             return x;
         };
         // geometry used by the prefetch (4 columns per lane, 8 steps) in TMA mode
@@ -573,7 +602,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         const bool want_prefetch = !tma_mode || p.epi.act == SVC_ACT_ROPE;
         if (cur.valid && want_prefetch && g_cur.vec && cur.t_base < p.T)
             epi_prefetch(p.epi, g_cur, lane, cur.b, cur.t_base, p.T, rr_cur);
+        int tr_i = 0;
+        const bool tr_on = (warp == 2 && lane == 0);
         while (cur.valid) {
+            if (tr_on) GTRACE(0, tr_i, 0);
             if (cur.ch == 0) {
                 mbar_wait(&tmem_full_bar[group], (cur.it >> 1) & 1);
                 tc_fence_after();
@@ -581,12 +613,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             uint32_t r[32], r2[EPI == 2 ? 32 : 1];
             tmem_ld_32x32(taddr + cur.ch * acc_per_item, r);
             if constexpr (EPI == 2) tmem_ld_32x32(taddr + cur.ch * 64 + 32, r2);
-            const Item nxt = cur.last ? make_item(cur.it + 2, 0) : make_item(cur.it, cur.ch + 1);
+            const Item nxt = next_item(cur);
             EpiChunk g_nxt = epi_chunk_geom(p.epi, nxt.n0c);
             if constexpr (tma_mode) { g_nxt = g_tma; g_nxt.c0 = pair ? (nxt.n0c >> 1) : nxt.n0c; }
-            if (nxt.valid && want_prefetch && g_nxt.vec && nxt.t_base < p.T)
+            if (nxt.valid && want_prefetch && g_nxt.vec && nxt.t_base < p.T && !(p.dbg & 32))
                 epi_prefetch(p.epi, g_nxt, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
+            if (tr_on) GTRACE(0, tr_i, 1);
             tc_wait_ld();
+            if (tr_on) GTRACE(0, tr_i, 2);
             if (cur.last) {                     // this warp has read its whole slice of the buffer
                 tc_fence_before();
                 __syncwarp();
@@ -611,6 +645,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     epilogue_item_tma<false>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
                 }
             }
+            if (tr_on) GTRACE(0, tr_i, 3);
+            ++tr_i;
             cur = nxt;
             g_cur = g_nxt;
 #pragma unroll
@@ -932,3 +968,10 @@ extern "C" int svc_gemm(const svc_gemm_desc* d, int backend, void* stream) {
     if (d->dtype == SVC_BF16 && backend == SVC_BACKEND_AUTO) return svc::gemm_tc(*d, st);
     return svc::gemm_simt(*d, st);
 }
+
+#ifdef SVC_TRACE
+extern "C" int svc_debug_gemm_trace(long long* host, int n) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host, svc::g_gemm_trace, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
+#endif
