@@ -74,6 +74,18 @@ __device__ __forceinline__ void reg_alloc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
+// Named barriers that alternate the exp2-heavy phase between the two softmax groups (the MUFU
+// pipe is shared per SM sub-partition: when both groups exponentiate at once each runs at half
+// rate and the pipe then idles while both store P / wait; alternating keeps it busy and puts one
+// group's load / store / barrier time under the other group's exp phase - FlashAttention-3's
+// ping-pong scheduling).  Barrier id 2+g is "group g may enter its exp phase".
+__device__ __forceinline__ void pingpong_wait(int g) {
+    asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
+}
+__device__ __forceinline__ void pingpong_signal(int g_other) {
+    asm volatile("bar.arrive %0, 256;" ::"r"(2 + g_other) : "memory");
+}
+
 // 32 lanes x 32 columns store (thread i writes row lane_base + i)
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -320,6 +332,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 need = true;
                 m_new = mx;
             }
+            pingpong_wait(g);                       // my turn on the MUFU pipe
             float la[4] = {0.f, 0.f, 0.f, 0.f};     // independent partial sums
             uint32_t pk[64];
 #pragma unroll
@@ -332,6 +345,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                     pk[c * 16 + (i >> 1)] = pack_bf16(p0, p1);
                 }
             const float l_blk = (la[0] + la[1]) + (la[2] + la[3]);
+            pingpong_signal(g ^ 1);                 // hand the MUFU pipe to the other group
             TRACE(1, j, 3);
             // PV of the previous block must have retired before P / O are touched
             mbar_wait(&p_empty[g], (j & 1) ^ 1);
@@ -366,6 +380,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             mbar_arrive(&p_full[g]);
             TRACE(1, j, 6);
         };
+        if (g == 1) pingpong_signal(0);             // group 0 goes first
         for (int j = 0; j < n_blocks - 1; ++j) block(j, std::false_type{});
         if (n_blocks * AT_BN > kv_len) block(n_blocks - 1, std::true_type{});
         else block(n_blocks - 1, std::false_type{});
