@@ -32,7 +32,7 @@ constexpr int AT_BM = 128;   // queries per Q tile (one TMEM lane each)
 constexpr int AT_QT = 2;     // Q tiles per CTA (ping-pong between two softmax groups)
 constexpr int AT_BN = 128;   // keys per block
 constexpr int AT_HD = 64;
-constexpr int AT_KST = 3;    // K / V ring depth
+constexpr int AT_KST = 4;    // K / V ring depth
 constexpr int AT_THREADS = 128 + AT_QT * 128;   // warpgroup 0: TMA, MMA, 2 idle warps; WG 1-2: softmax
 
 struct alignas(64) AttnTcParams {
@@ -49,8 +49,7 @@ struct AttnSmem {
     static constexpr int Q_OFF = 0;
     static constexpr int K_OFF = Q_OFF + AT_QT * TILE;
     static constexpr int V_OFF = K_OFF + AT_KST * TILE;
-    static constexpr int P_OFF = V_OFF + AT_KST * TILE;     // per group: 2 tiles of 128 x 64
-    static constexpr int BAR_OFF = P_OFF + AT_QT * 2 * TILE;
+    static constexpr int BAR_OFF = V_OFF + AT_KST * TILE;
     static constexpr int TOTAL = BAR_OFF + 512 + 1024;
 };
 
@@ -168,6 +167,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_S = tmem_base;                    // AT_QT x 128 columns
     const uint32_t tmem_O = tmem_base + AT_QT * AT_BN;    // AT_QT x 64 columns
+    const uint32_t tmem_P = tmem_O + AT_QT * AT_HD;       // AT_QT x 64 columns: P as packed bf16 pairs
 
     // warpgroup 0 (TMA, MMA, two idle warps) hands its registers to the two softmax warpgroups
     if (warp == 0) {
@@ -211,7 +211,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             // descriptor lo words of the smem regions (address field only varies)
             const uint32_t q_lo0 = desc_lo(smem_u32(smem + S::Q_OFF));
             const uint32_t k_lo0 = desc_lo(smem_u32(smem + S::K_OFF));
-            const uint32_t p_lo0 = desc_lo(smem_u32(smem + S::P_OFF));
             const uint32_t v_lo0 = desc_lo(smem_u32(smem + S::V_OFF), 1024);   // MN-major: LBO = 1024
             auto issue_s = [&](int g, int j) {
                 const int st = j % AT_KST;
@@ -233,13 +232,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 if (g == 1) TRACE(3, j, 0);
                 tc_fence_after();
                 if (g == 1) TRACE(3, j, 1);
-                const uint32_t plo = p_lo0 + g * (2 * S::TILE >> 4);
                 const uint32_t vlo = v_lo0 + st * (S::TILE >> 4);
 #pragma unroll
-                for (int k = 0; k < AT_BN / 16; ++k)
-                    tc_mma_f16_lh(tmem_O + g * AT_HD, plo + (k >> 2) * (S::TILE >> 4) + (k & 3) * 2,
-                                  kDescHiSw128, vlo + k * (2048 >> 4), kDescHiSw128, idesc_o,
-                                  (j | k) != 0);
+                for (int k = 0; k < AT_BN / 16; ++k)      // A = P from TMEM: 8 columns per 16 keys
+                    tc_mma_f16_ts(tmem_O + g * AT_HD, tmem_P + g * (AT_BN / 2) + k * 8,
+                                  vlo + k * (2048 >> 4), kDescHiSw128, idesc_o, (j | k) != 0);
                 if (g == 1) TRACE(3, j, 2);
                 tc_commit(&p_empty[g]);
                 if (g == AT_QT - 1) TRACE(0, j, 6);
@@ -281,7 +278,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         const uint32_t tO = tmem_O + g * AT_HD + lane_addr;
         constexpr float kLog2e = 1.4426950408889634f;
         constexpr float kThresh = 8.0f;       // in log2 units
-        uint8_t* pbuf = smem + S::P_OFF + g * 2 * S::TILE + row * 128;
+        const uint32_t tP = tmem_P + g * (AT_BN / 2) + lane_addr;
         float m_ref = 0.f, l_run = 0.f;       // m_ref in log2 units (already * log2e)
 
         // one KV block of this row; TAIL = the block holds keys >= kv_len (masked), only the last one
@@ -367,15 +364,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             }
             m_ref = m_new;
             l_run += l_blk;
-            // P row: 128 keys = 2 tiles x 8 chunks of 16 B, 128B-swizzled (chunk ^ (row & 7))
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                uint8_t* tile = pbuf + (q >> 3) * S::TILE;
-                *reinterpret_cast<uint4*>(tile + (((q & 7) ^ (row & 7)) << 4)) =
-                    make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            // P row: 128 keys as 64 packed bf16 pairs -> this row's lane of the P columns in TMEM
+            {
+                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
+                uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
+                tmem_st_32x32(tP, lo);
+                tmem_st_32x32(tP + 32, hi);
+                tc_wait_st();
             }
             TRACE(1, j, 5);
-            fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(&p_full[g]);
             TRACE(1, j, 6);
