@@ -48,6 +48,30 @@ def build_trace() -> str:
     return out
 
 
+def build_variant(tag: str, defines, sources=("attention.cu",)) -> str:
+    """Experiment build: recompile ``sources`` with extra -D flags, link with the regular objects of
+    the other files into libseedvc_b200_<tag>.so (select it with SEEDVC_B200_LIB). Never shipped."""
+    build()
+    out = os.path.join(PKG, f"libseedvc_b200_{tag}.so")
+    objs = []
+    for s in SOURCES:
+        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
+        if s in sources:
+            obj = os.path.join(CSRC, s.replace(".cu", f".{tag}.o"))
+            cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + \
+                [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, s), "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(r.stderr)
+        objs.append(obj)
+    r = subprocess.run([_nvcc(), "-shared", "-o", out] + objs +
+                       ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "seedvc_b200.h"))
@@ -79,7 +103,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    if "--trace" in sys.argv:
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    elif "--trace" in sys.argv:
         print(build_trace())
     else:
         print(build(force="--force" in sys.argv, verbose=True))

@@ -29,11 +29,17 @@ __device__ long long g_attn_trace[4][64][8];   // [role][block][event] clock64 s
 #endif
 
 constexpr int AT_BM = 128;   // queries per Q tile (one TMEM lane each)
-constexpr int AT_QT = 2;     // Q tiles per CTA (ping-pong between two softmax groups)
-constexpr int AT_BN = 128;   // keys per block
+constexpr int AT_QT = 3;     // Q tiles per CTA = softmax groups taking turns on the MUFU pipe
+constexpr int AT_BN = 64;    // keys per block
 constexpr int AT_HD = 64;
-constexpr int AT_KST = 4;    // K / V ring depth
-constexpr int AT_THREADS = 128 + AT_QT * 128;   // warpgroup 0: TMA, MMA, 2 idle warps; WG 1-2: softmax
+#ifndef AT_KST_V
+#define AT_KST_V 6
+#endif
+#ifndef AT_SM_REGS
+#define AT_SM_REGS 152
+#endif
+constexpr int AT_KST = AT_KST_V;    // K / V ring depth
+constexpr int AT_THREADS = 128 + AT_QT * 128;   // warpgroup 0: TMA + one MMA issuer per Q tile; then one softmax warpgroup per tile
 
 struct alignas(64) AttnTcParams {
     CUtensorMap qmap, kmap, vmap;  // (H*64, T, B) bf16 views, box {64, 128, 1}
@@ -45,11 +51,12 @@ struct alignas(64) AttnTcParams {
 };
 
 struct AttnSmem {
-    static constexpr int TILE = AT_BM * AT_HD * 2;          // 16 KB
+    static constexpr int QTILE = AT_BM * AT_HD * 2;         // 16 KB
+    static constexpr int KTILE = AT_BN * AT_HD * 2;         // 8 KB
     static constexpr int Q_OFF = 0;
-    static constexpr int K_OFF = Q_OFF + AT_QT * TILE;
-    static constexpr int V_OFF = K_OFF + AT_KST * TILE;
-    static constexpr int BAR_OFF = V_OFF + AT_KST * TILE;
+    static constexpr int K_OFF = Q_OFF + AT_QT * QTILE;
+    static constexpr int V_OFF = K_OFF + AT_KST * KTILE;
+    static constexpr int BAR_OFF = V_OFF + AT_KST * KTILE;
     static constexpr int TOTAL = BAR_OFF + 512 + 1024;
 };
 
@@ -73,17 +80,6 @@ __device__ __forceinline__ void reg_alloc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
-// Named barriers that alternate the exp2-heavy phase between the two softmax groups (the MUFU
-// pipe is shared per SM sub-partition: when both groups exponentiate at once each runs at half
-// rate and the pipe then idles while both store P / wait; alternating keeps it busy and puts one
-// group's load / store / barrier time under the other group's exp phase - FlashAttention-3's
-// ping-pong scheduling).  Barrier id 2+g is "group g may enter its exp phase".
-__device__ __forceinline__ void pingpong_wait(int g) {
-    asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
-}
-__device__ __forceinline__ void pingpong_signal(int g_other) {
-    asm volatile("bar.arrive %0, 256;" ::"r"(2 + g_other) : "memory");
-}
 
 // 32 lanes x 32 columns store (thread i writes row lane_base + i)
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -99,15 +95,21 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         : "memory");
 }
 
-// One CTA = 256 queries (two Q tiles) of one (batch, head).
-//   warp 0    : TMA producer (Q tiles once, K_j / V_j through mbarrier rings, shared by both tiles)
-//   warp 1    : MMA issuer: S_g = Q_g K_j^T (TMEM, 128 cols per group) and O_g += P_g V_j (TMEM,
-//               64 cols per group, accumulated in place), ordered PV0_j, S0_{j+1}, PV1_j, S1_{j+1}
-//               so the tensor pipe works for one group while the other group is in softmax
-//   warps 2-5 / 6-9 : softmax group 0 / 1, one query row per thread: whole S row to registers in
-//               one tcgen05.ld pass, exp2 against a reference max that is only moved when the
-//               row max grows by more than 2^8 (then O in TMEM and l are rescaled, rare),
-//               P -> bf16 -> 128B-swizzled smem for the PV MMA.
+// One CTA = AT_QT x 128 = 384 queries (three Q tiles) of one (batch, head); keys in blocks of 64.
+//   warp 0    : TMA producer (Q tiles once, K_j / V_j through mbarrier rings shared by the tiles)
+//   warps 1-3 : one MMA-issuing thread per Q tile g: S_g = Q_g K_j^T (TMEM, 64 columns) and
+//               O_g += P_g V_j (TMEM, 64 columns, accumulated in place; A operand = P_g read
+//               straight from TMEM, B = V_j MN-major from shared memory).  Each tile runs its own
+//               S / PV chain, so no tile waits behind another tile's barriers.
+//   warps 4-15: softmax group g = (warp - 4) / 4, one query row per thread: S row to registers in
+//               one tcgen05.ld pass, exp2 (packed f32x2 FFMA / FADD around MUFU.EX2) against a
+//               reference max that is only moved when the row max grows by more than 2^8 (then O
+//               in TMEM and l are rescaled, rare), P -> packed bf16 pairs -> tcgen05.st into the
+//               tile's P columns (no shared-memory round trip, no proxy fence).
+// TMEM columns: S 3 x 64 | O 3 x 64 | P 3 x 32 = 480 of 512.  The softmax is bound by the MUFU
+// pipe (8 cycles per warp instruction per SM sub-partition, measured: scripts/ubench/mufu.cu)
+// and by the fixed latencies of a block (barrier round trips, tcgen05.ld/st); three free-running
+// groups per SM keep that pipe ~70% busy, where two groups taking turns reached 60%.
 __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
     using S = AttnSmem;
     extern __shared__ uint8_t smem_raw[];
@@ -167,15 +169,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_S = tmem_base;                    // AT_QT x 128 columns
     const uint32_t tmem_O = tmem_base + AT_QT * AT_BN;    // AT_QT x 64 columns
-    const uint32_t tmem_P = tmem_O + AT_QT * AT_HD;       // AT_QT x 64 columns: P as packed bf16 pairs
+    const uint32_t tmem_P = tmem_O + AT_QT * AT_HD;       // AT_QT x AT_BN/2 columns: P as packed bf16 pairs
 
-    // warpgroup 0 (TMA, MMA, two idle warps) hands its registers to the two softmax warpgroups
+    // warpgroup 0 (TMA, MMA issuers) hands its registers to the softmax warpgroups
     if (warp == 0) {
         reg_dealloc<40>();
         if (lane == 0) {
-            mbar_expect_tx(q_full, AT_QT * S::TILE);
+            mbar_expect_tx(q_full, AT_QT * S::QTILE);
             for (int g = 0; g < AT_QT; ++g)
-                tma_load_3d(smem + S::Q_OFF + g * S::TILE, &p.qmap, q_full, h * AT_HD, q0 + g * AT_BM, b);
+                tma_load_3d(smem + S::Q_OFF + g * S::QTILE, &p.qmap, q_full, h * AT_HD, q0 + g * AT_BM, b);
             for (int j = 0; j < n_blocks; ++j) {
                 const int st = j % AT_KST;
                 const uint32_t ph = (j / AT_KST) & 1;
@@ -183,15 +185,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #ifdef SVC_TRACE
                 if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) g_attn_trace[0][j][3] = clock64();
 #endif
-                mbar_expect_tx(&k_full[st], S::TILE);
-                tma_load_3d(smem + S::K_OFF + st * S::TILE, &p.kmap, &k_full[st], h * AT_HD,
+                mbar_expect_tx(&k_full[st], S::KTILE);
+                tma_load_3d(smem + S::K_OFF + st * S::KTILE, &p.kmap, &k_full[st], h * AT_HD,
                             j * AT_BN, b);
                 mbar_wait(&v_empty[st], ph ^ 1);
 #ifdef SVC_TRACE
                 if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) g_attn_trace[0][j][4] = clock64();
 #endif
-                mbar_expect_tx(&v_full[st], S::TILE);
-                tma_load_3d(smem + S::V_OFF + st * S::TILE, &p.vmap, &v_full[st], h * AT_HD,
+                mbar_expect_tx(&v_full[st], S::KTILE);
+                tma_load_3d(smem + S::V_OFF + st * S::KTILE, &p.vmap, &v_full[st], h * AT_HD,
                             j * AT_BN, b);
 #ifdef SVC_TRACE
                 if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) {
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #endif
             }
         }
-    } else if (warp == 1 || warp == 2) {
+    } else if (warp >= 1 && warp <= AT_QT) {
         reg_dealloc<40>();
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
@@ -217,8 +219,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 if (g == 0) TRACE(0, j, 2);
                 if (g == 1) TRACE(3, j, 3);
                 tc_fence_after();
-                const uint32_t qlo = q_lo0 + g * (S::TILE >> 4);
-                const uint32_t klo = k_lo0 + st * (S::TILE >> 4);
+                const uint32_t qlo = q_lo0 + g * (S::QTILE >> 4);
+                const uint32_t klo = k_lo0 + st * (S::KTILE >> 4);
 #pragma unroll
                 for (int k = 0; k < AT_HD / 16; ++k)
                     tc_mma_f16_lh(tmem_S + g * AT_BN, qlo + k * 2, kDescHiSw128, klo + k * 2, kDescHiSw128,
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 if (g == 1) TRACE(3, j, 0);
                 tc_fence_after();
                 if (g == 1) TRACE(3, j, 1);
-                const uint32_t vlo = v_lo0 + st * (S::TILE >> 4);
+                const uint32_t vlo = v_lo0 + st * (S::KTILE >> 4);
 #pragma unroll
                 for (int k = 0; k < AT_BN / 16; ++k)      // A = P from TMEM: 8 columns per 16 keys
                     tc_mma_f16_ts(tmem_O + g * AT_HD, tmem_P + g * (AT_BN / 2) + k * 8,
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         reg_dealloc<40>();
     } else {
         // ===================== softmax groups: one query row per thread =====================
-        reg_alloc<224>();
+        reg_alloc<AT_QT == 2 ? 224 : AT_SM_REGS>();
         const int g = (warp - 4) >> 2;
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
@@ -288,11 +290,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             mbar_wait(&s_full[g], j & 1);
             TRACE(1, j, 1);
             tc_fence_after();
-            float s[4][32];
+            constexpr int NC = AT_BN / 32;
+            float s[NC][32];
             {
-                uint32_t r[4][32];
+                uint32_t r[NC][32];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) tmem_ld_32x32(tS + c * 32, r[c]);
+                for (int c = 0; c < NC; ++c) tmem_ld_32x32(tS + c * 32, r[c]);
                 tc_wait_ld();
                 TRACE(1, j, 2);
 #ifdef SVC_TRACE
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 mbar_arrive(&s_empty[g]);
                 const int kbase = j * AT_BN;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < NC; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         s[c][i] = __uint_as_float(r[c][i]);
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < 8; ++i) mxa[i] = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < NC; ++c)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], s[c][i]);
             float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
@@ -329,20 +332,21 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 need = true;
                 m_new = mx;
             }
-            pingpong_wait(g);                       // my turn on the MUFU pipe
-            float la[4] = {0.f, 0.f, 0.f, 0.f};     // independent partial sums
-            uint32_t pk[64];
+            // packed f32x2 arithmetic: one FFMA2 / FADD2 per pair of keys
+            float2 la2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+            const float2 sc2 = make_float2(kLog2e, kLog2e), mn2 = make_float2(-m_new, -m_new);
+            uint32_t pk[AT_BN / 2];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < NC; ++c)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    const float p0 = fast_exp2(fmaf(s[c][i], kLog2e, -m_new));
-                    const float p1 = fast_exp2(fmaf(s[c][i + 1], kLog2e, -m_new));
-                    la[(i >> 1) & 3] += p0 + p1;
-                    pk[c * 16 + (i >> 1)] = pack_bf16(p0, p1);
+                    const float2 x = __ffma2_rn(make_float2(s[c][i], s[c][i + 1]), sc2, mn2);
+                    const float2 pp = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                    la2[(i >> 1) & 3] = __fadd2_rn(la2[(i >> 1) & 3], pp);
+                    pk[c * 16 + (i >> 1)] = pack_bf16(pp.x, pp.y);
                 }
-            const float l_blk = (la[0] + la[1]) + (la[2] + la[3]);
-            pingpong_signal(g ^ 1);                 // hand the MUFU pipe to the other group
+            const float2 l2 = __fadd2_rn(__fadd2_rn(la2[0], la2[1]), __fadd2_rn(la2[2], la2[3]));
+            const float l_blk = l2.x + l2.y;
             TRACE(1, j, 3);
             // PV of the previous block must have retired before P / O are touched
             mbar_wait(&p_empty[g], (j & 1) ^ 1);
@@ -364,20 +368,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             }
             m_ref = m_new;
             l_run += l_blk;
-            // P row: 128 keys as 64 packed bf16 pairs -> this row's lane of the P columns in TMEM
-            {
-                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
-                uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
-                tmem_st_32x32(tP, lo);
-                tmem_st_32x32(tP + 32, hi);
-                tc_wait_st();
-            }
+            // P row: AT_BN keys as packed bf16 pairs -> this row's lane of the P columns in TMEM
+#pragma unroll
+            for (int c = 0; c < AT_BN / 64; ++c)
+                tmem_st_32x32(tP + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&pk[c * 32]));
+            tc_wait_st();
             TRACE(1, j, 5);
             tc_fence_before();
             mbar_arrive(&p_full[g]);
             TRACE(1, j, 6);
         };
-        if (g == 1) pingpong_signal(0);             // group 0 goes first
         for (int j = 0; j < n_blocks - 1; ++j) block(j, std::false_type{});
         if (n_blocks * AT_BN > kv_len) block(n_blocks - 1, std::true_type{});
         else block(n_blocks - 1, std::false_type{});
