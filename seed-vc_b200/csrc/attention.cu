@@ -35,6 +35,9 @@ constexpr int AT_HD = 64;
 #ifndef AT_KST_V
 #define AT_KST_V 6
 #endif
+#ifndef AT_POLY_EVERY
+#define AT_POLY_EVERY 3   // every 3rd key pair takes the FMA-pipe exp2 (0 = all on MUFU)
+#endif
 #ifndef AT_SM_REGS
 #define AT_SM_REGS 152
 #endif
@@ -69,6 +72,25 @@ __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// 2^x for a pair of values on the FMA pipe (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5],
+// degree-3 minimax polynomial (relative error 7.5e-5, far below the bf16 rounding of P), exponent
+// inserted with an integer add.  Inputs <= -126 flush to 2^-126.
+__device__ __forceinline__ float2 poly_exp2_x2(float2 x) {
+    const float kMagic = 12582912.f;   // 1.5 * 2^23: x + kMagic rounds x to an integer in the low mantissa bits
+    x.x = fmaxf(x.x, -126.f);
+    x.y = fmaxf(x.y, -126.f);
+    const float2 t = __fadd2_rn(x, make_float2(kMagic, kMagic));
+    const float2 n = __fadd2_rn(t, make_float2(-kMagic, -kMagic));
+    const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+    float2 p = __ffma2_rn(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+    p = __ffma2_rn(p, f, make_float2(0.6932609677f, 0.6932609677f));
+    p = __ffma2_rn(p, f, make_float2(0.9999280572f, 0.9999280572f));
+    float2 r;
+    r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+    r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+    return r;
 }
 
 template <int N>
@@ -313,40 +335,52 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                         if (TAIL && kbase + c * 32 + i >= kv_len) s[c][i] = -INFINITY;
                     }
             }
-            // row max with 8 independent chains (a single fmax chain is 128 x 4 cycles of latency)
-            float mxa[8];
+            // row max with 8 independent chains (a single fmax chain is AT_BN x 4 cycles of latency)
+            auto rowmax = [&]() {
+                float mxa[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) mxa[i] = -INFINITY;
+                for (int i = 0; i < 8; ++i) mxa[i] = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < NC; ++c)
+                for (int c = 0; c < NC; ++c)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], s[c][i]);
-            float mx = fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
-                             fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
-            mx *= kLog2e;
+                    for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], s[c][i]);
+                return kLog2e * fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
+                                      fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+            };
+            // p = 2^(s * log2e - m) for the block, packed to bf16 pairs; returns the row sum.
+            // Packed f32x2 arithmetic: one FFMA2 / FADD2 per pair of keys.
+            uint32_t pk[AT_BN / 2];
+            auto exps = [&](float m) {
+                float2 la2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+                const float2 sc2 = make_float2(kLog2e, kLog2e), mn2 = make_float2(-m, -m);
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float2 x = __ffma2_rn(make_float2(s[c][i], s[c][i + 1]), sc2, mn2);
+#if AT_POLY_EVERY > 0
+                        float2 pp;
+                        if (!TAIL && ((i >> 1) % AT_POLY_EVERY) == AT_POLY_EVERY - 1) pp = poly_exp2_x2(x);
+                        else pp = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+#else
+                        const float2 pp = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+#endif
+                        la2[(i >> 1) & 3] = __fadd2_rn(la2[(i >> 1) & 3], pp);
+                        pk[c * 16 + (i >> 1)] = pack_bf16(pp.x, pp.y);
+                    }
+                const float2 l2 = __fadd2_rn(__fadd2_rn(la2[0], la2[1]), __fadd2_rn(la2[2], la2[3]));
+                return l2.x + l2.y;
+            };
             bool need = false;
-            float m_new = m_ref;
+            float m_new = m_ref, l_blk;
+            const float mx = rowmax();
             if (j == 0) {
                 m_new = mx;
             } else if (mx > m_ref + kThresh) {
                 need = true;
                 m_new = mx;
             }
-            // packed f32x2 arithmetic: one FFMA2 / FADD2 per pair of keys
-            float2 la2[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-            const float2 sc2 = make_float2(kLog2e, kLog2e), mn2 = make_float2(-m_new, -m_new);
-            uint32_t pk[AT_BN / 2];
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float2 x = __ffma2_rn(make_float2(s[c][i], s[c][i + 1]), sc2, mn2);
-                    const float2 pp = make_float2(fast_exp2(x.x), fast_exp2(x.y));
-                    la2[(i >> 1) & 3] = __fadd2_rn(la2[(i >> 1) & 3], pp);
-                    pk[c * 16 + (i >> 1)] = pack_bf16(pp.x, pp.y);
-                }
-            const float2 l2 = __fadd2_rn(__fadd2_rn(la2[0], la2[1]), __fadd2_rn(la2[2], la2[3]));
-            const float l_blk = l2.x + l2.y;
+            l_blk = exps(m_new);
             TRACE(1, j, 3);
             // PV of the previous block must have retired before P / O are touched
             mbar_wait(&p_empty[g], (j & 1) ^ 1);
