@@ -297,6 +297,16 @@ def run_ours(a):
                     "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
                     "share_of_step": round(g["ms"] / tot, 3), "launches_per_step": g["launches"],
                     "avg_launch_ms": round(g["ms"] / g["launches"], 4), "traffic": None}
+            # DRAM bytes per launch from the committed ncu pass over one config-2 conversion
+            # (profiles/*_gemm_traffic.json, scripts/gpu_ncu.sh); only valid for that workload
+            tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_gemm_traffic.json")) \
+                if os.path.isdir(os.path.join(ROOT, "profiles")) else []
+            if tfiles and a.workload == "config2":
+                with open(os.path.join(ROOT, "profiles", tfiles[-1])) as f:
+                    tj = json.load(f)
+                if tj.get("launches") == g["launches"]:
+                    roof["traffic"] = round(tj["traffic_bytes_per_launch"])
+                    roof["traffic_unit"] = "bytes per launch (ncu dram read+write, " + tfiles[-1] + ")"
 
     if rank != 0:
         if world > 1:

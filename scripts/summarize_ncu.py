@@ -41,16 +41,44 @@ if os.path.exists(path):
         a[1] += ms
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(PROF, f"{tag}_launch_list_summary.md"), "w") as f:
+        cmdf = os.path.join(OUT, "launches.cmd")
+        cmd = open(cmdf).read().strip() if os.path.exists(cmdf) else "(see scripts/gpu_ncu.sh)"
         f.write(f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none)\n\n"
-                "Command: `python bench.py --workload profile --steps 1 --warmup 1 --no-cpu-baseline "
-                "--no-profile` (config-2 shapes: whisper-small DiT + BigVGAN-22k, B=8, T=2580, 2 Euler "
-                "steps per conversion).  Times under ncu are cold-cache and serialised: compare SHARES.\n"
-                "`at::*` rows are one-time weight preparation / input staging done by torch at setup.\n\n"
+                f"Command: `{cmd}`\n\nOne whole conversion pass of the bench's default workload (config 2: "
+                "whisper-small DiT + BigVGAN-22k, B=32, T=2580, 25 Euler steps), our kernels only (torch's "
+                "one-time weight preparation filtered out).  Times under ncu are cold-cache and serialised: "
+                "compare SHARES with `kernel_breakdown` / `roofline.share_of_step` of the bench line.\n\n"
                 "| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {a[0]} | {a[1]:.3f} | {a[1] / tot:.3f} |\n")
         f.write(f"\nTotal {tot:.2f} ms over {sum(a[0] for a in agg.values())} launches.\n")
     print("wrote launch list summary")
+
+# ---- DRAM traffic of every gemm_tc launch of one config-2 pass --------------------------------
+path = os.path.join(OUT, "gemm_traffic.csv")
+if os.path.exists(path):
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    tot = collections.defaultdict(float)
+    ids = set()
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"].lower()
+        scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-6, "nsecond": 1e-6,
+                 "us": 1e-3, "usecond": 1e-3, "ms": 1, "msecond": 1}.get(u, 1)
+        tot[row["Metric Name"]] += v * scale
+        ids.add(row["ID"])
+    n = len(ids)
+    out = {"kernel": "gemm_tc_kernel", "launches": n,
+           "command": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum "
+                      "--clock-control none -k regex:gemm_tc_kernel -c 2142 python bench.py --steps 1 "
+                      "--warmup 1 --no-cpu-baseline --no-profile (first conversion pass of config 2)",
+           "dram_read_bytes": tot["dram__bytes_read.sum"], "dram_write_bytes": tot["dram__bytes_write.sum"],
+           "traffic_bytes_per_launch": (tot["dram__bytes_read.sum"] + tot["dram__bytes_write.sum"]) / max(n, 1),
+           "ncu_ms_total": tot["gpu__time_duration.sum"]}
+    with open(os.path.join(PROF, f"{tag}_gemm_traffic.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote gemm traffic", out["launches"], "launches")
 
 # ---- full captures ---------------------------------------------------------------------------
 for rep in sorted(os.listdir(OUT)):
