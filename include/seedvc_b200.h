@@ -94,6 +94,10 @@ typedef struct svc_gemm_desc {
     long long of_bstride, of_rstride;
     void* out_op; /* operand dtype, or NULL */
     long long oo_bstride, oo_rstride;
+    /* optional pair-major copy of rope_tab: (32 pairs, rope_ld positions, 2); lets the tensor-core
+       path rotate in the accumulator's row layout with coalesced table reads.  NULL = not given. */
+    const float* rope_tab_t;
+    int rope_ld;
 } svc_gemm_desc;
 
 int svc_gemm(const svc_gemm_desc* d, int backend, void* stream);

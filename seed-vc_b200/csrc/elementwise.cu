@@ -369,4 +369,4 @@ void svc_set_error(const char* msg) {
     g_err[sizeof(g_err) - 1] = 0;
 }
 extern "C" const char* svc_last_error(void) { return g_err; }
-extern "C" int svc_version(void) { return 100; }
+extern "C" int svc_version(void) { return 101; }

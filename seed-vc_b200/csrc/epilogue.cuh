@@ -12,6 +12,8 @@ struct EpiParams {
     const float* rowbias;
     long long rowbias_bstride;
     const float* rope_tab;
+    const float* rope_tab_t;   // pair-major (32, rope_ld, 2) copy, or nullptr
+    int rope_ld;
     int rope_cols, rope_pos0, q_cols;
     float q_scale;
     const float* gate;
@@ -38,6 +40,8 @@ inline EpiParams make_epi_params(const svc_gemm_desc& d) {
     e.rowbias = d.rowbias;
     e.rowbias_bstride = d.rowbias_bstride;
     e.rope_tab = d.rope_tab;
+    e.rope_tab_t = d.rope_tab_t;
+    e.rope_ld = d.rope_ld;
     e.rope_cols = d.rope_cols;
     e.rope_pos0 = d.rope_pos0;
     e.q_cols = d.q_cols;

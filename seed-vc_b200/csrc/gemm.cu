@@ -40,7 +40,8 @@ struct alignas(64) TcParams {
     // TMA-store epilogue: 0 = off (register/LSU epilogue), 1 = bf16 tile -> out_op,
     // 2 = fp32 tile reduce-added into out_f32 (in-place residual), 3 = fp32 tile -> out_f32
     int store_mode;
-    CUtensorMap omap;          // (N_out, T, B) view of the output, box {32, 32, 1}, no swizzle
+    int direct;                // 1: row-layout epilogue writes the swizzled TMA tile directly (no transpose)
+    CUtensorMap omap;          // (N_out, T, B) view of the output, box {32, 32, 1}; swizzled when direct
     EpiParams epi;
 };
 
@@ -431,6 +432,114 @@ __device__ __forceinline__ void epilogue_item_tma(const TcParams& p, float* stag
     }
 }
 
+// (cos, sin) of the 16 pairs of a 32-column item for this lane's row, from the pair-major table:
+// consecutive lanes = consecutive positions = consecutive addresses
+__device__ __forceinline__ void rope_prefetch_rows(const EpiParams& e, int c0, int lane, int t_base,
+                                                   float4 (&rr)[8]) {
+    const int pos = min(e.rope_pos0 + t_base + lane, e.rope_ld - 1);
+    const float2* tab = reinterpret_cast<const float2*>(e.rope_tab_t) +
+                        static_cast<long long>((c0 & 63) >> 1) * e.rope_ld + pos;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float2 a = __ldg(tab + static_cast<long long>(2 * i) * e.rope_ld);
+        const float2 b = __ldg(tab + static_cast<long long>(2 * i + 1) * e.rope_ld);
+        rr[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+
+// Direct TMA-store epilogue: the whole item is finished in the TMEM row layout (thread = output row,
+// 32 consecutive output columns in registers; per-column operands are warp-uniform loads) and written
+// once into a swizzled shared-memory tile that the TMA store reads (bf16: 64B rows, SWIZZLE_64B; fp32:
+// 128B rows, SWIZZLE_128B) - no transpose round trip through shared memory.  Interleaved-pair RoPE
+// works here because a pair sits in adjacent registers; its table must be pair-major so that the 32
+// rows of a warp read consecutive addresses (rr = 16 (cos, sin) pairs prefetched one item ahead).
+template <bool PAIR>
+__device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* stage, int lane, int b,
+                                                     int t_base, int n0_acc, float (&v)[PAIR ? 64 : 32],
+                                                     const float4 (&rr)[8]) {
+    const EpiParams& e = p.epi;
+    constexpr int NA = PAIR ? 64 : 32;
+    const int c0 = PAIR ? (n0_acc >> 1) : n0_acc;          // first output column
+    if (e.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < NA; j += 4)
+            if (n0_acc + j < e.N) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(e.bias + n0_acc + j));
+                v[j] += q.x, v[j + 1] += q.y, v[j + 2] += q.z, v[j + 3] += q.w;
+            }
+    }
+    if (e.rowbias != nullptr) {
+        const float* rb = e.rowbias + static_cast<long long>(b) * e.rowbias_bstride + n0_acc;
+#pragma unroll
+        for (int j = 0; j < NA; j += 4)
+            if (n0_acc + j < e.N) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(rb + j));
+                v[j] += q.x, v[j + 1] += q.y, v[j + 2] += q.z, v[j + 3] += q.w;
+            }
+    }
+    if (e.act == SVC_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(v[j]);
+    } else if (PAIR && e.act == SVC_ACT_SWIGLU_PAIR) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[2 * j] * fast_sigmoid(v[2 * j]) * v[2 * j + 1];
+    } else if (PAIR && e.act == SVC_ACT_TANH_SIG_PAIR) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[2 * j]) * fast_sigmoid(v[2 * j + 1]);
+    } else if (!PAIR && e.act == SVC_ACT_ROPE && c0 < e.rope_cols) {
+        const float qs = c0 < e.q_cols ? e.q_scale : 1.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 cs = rr[i];           // (cos, sin) of pairs 2i, 2i+1
+            const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+            v[4 * i] = (x0 * cs.x - x1 * cs.y) * qs;
+            v[4 * i + 1] = (x1 * cs.x + x0 * cs.y) * qs;
+            v[4 * i + 2] = (x2 * cs.z - x3 * cs.w) * qs;
+            v[4 * i + 3] = (x3 * cs.z + x2 * cs.w) * qs;
+        }
+    }
+    if (e.gate != nullptr) {
+        const float* gp = e.gate + static_cast<long long>(b) * e.gate_bstride + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            if (c0 + j < e.N_out) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(gp + j));
+                v[j] *= q.x, v[j + 1] *= q.y, v[j + 2] *= q.z, v[j + 3] *= q.w;
+            }
+    }
+    if (e.alpha != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+    }
+    // the previous TMA store of this warp must have finished reading the staging tile
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+    uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
+    if (p.store_mode == 1) {
+        uint8_t* row = sb + lane * 64;
+        const int sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(row + ((q ^ sw) << 4)) =
+                make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+    } else {
+        uint8_t* row = sb + lane * 128;
+        const int sw = lane & 7;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(row + ((q ^ sw) << 4)) =
+                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        if (p.store_mode == 2) tma_reduce_add_3d(&p.omap, stage, c0, t_base, b);
+        else tma_store_3d(&p.omap, stage, c0, t_base, b);
+        bulk_commit();
+    }
+}
+
 // Persistent, warp-specialised tcgen05 GEMM.  One CTA per SM walks output tiles
 // (n fastest, so CTAs running together share the A tile in L2); the accumulator is
 // double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.
@@ -559,8 +668,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         float* stage_buf = reinterpret_cast<float*>(smem + S::EPI_OFFSET) + ew * 32 * kStageRowF;
         const uint32_t taddr = tmem_base + group * ACC_COLS + (static_cast<uint32_t>(lg * 32) << 16);
         constexpr bool tma_mode = EPI != 0;
-        constexpr bool pair = EPI == 2;
-        constexpr int acc_per_item = EPI == 2 ? 64 : 32;   // accumulator columns per work item
+        constexpr bool pair = EPI == 2 || EPI == 4;
+        constexpr bool direct = EPI >= 3;
+        constexpr int acc_per_item = pair ? 64 : 32;   // accumulator columns per work item
         struct Item {
             int it, ch, b, t_base, n0c, ncols;
             bool valid, last;
@@ -599,9 +709,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         EpiChunk g_cur = epi_chunk_geom(p.epi, cur.n0c);
         if constexpr (tma_mode) { g_cur = g_tma; g_cur.c0 = pair ? (cur.n0c >> 1) : cur.n0c; }
         float4 rr_cur[8], rr_nxt[8];
-        const bool want_prefetch = !tma_mode || p.epi.act == SVC_ACT_ROPE;
+        const bool want_prefetch = !direct && (!tma_mode || p.epi.act == SVC_ACT_ROPE);
+        const bool rope_direct = direct && p.epi.act == SVC_ACT_ROPE;
         if (cur.valid && want_prefetch && g_cur.vec && cur.t_base < p.T)
             epi_prefetch(p.epi, g_cur, lane, cur.b, cur.t_base, p.T, rr_cur);
+        if (rope_direct && cur.valid && cur.n0c < p.epi.rope_cols)
+            rope_prefetch_rows(p.epi, cur.n0c, lane, cur.t_base, rr_cur);
         int tr_i = 0;
         const bool tr_on = (warp == 2 && lane == 0);
         while (cur.valid) {
@@ -610,14 +723,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 mbar_wait(&tmem_full_bar[group], (cur.it >> 1) & 1);
                 tc_fence_after();
             }
-            uint32_t r[32], r2[EPI == 2 ? 32 : 1];
+            uint32_t r[32], r2[pair ? 32 : 1];
             tmem_ld_32x32(taddr + cur.ch * acc_per_item, r);
-            if constexpr (EPI == 2) tmem_ld_32x32(taddr + cur.ch * 64 + 32, r2);
+            if constexpr (pair) tmem_ld_32x32(taddr + cur.ch * 64 + 32, r2);
             const Item nxt = next_item(cur);
             EpiChunk g_nxt = epi_chunk_geom(p.epi, nxt.n0c);
             if constexpr (tma_mode) { g_nxt = g_tma; g_nxt.c0 = pair ? (nxt.n0c >> 1) : nxt.n0c; }
             if (nxt.valid && want_prefetch && g_nxt.vec && nxt.t_base < p.T && !(p.dbg & 32))
                 epi_prefetch(p.epi, g_nxt, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
+            if (rope_direct && nxt.valid && nxt.n0c < p.epi.rope_cols)
+                rope_prefetch_rows(p.epi, nxt.n0c, lane, nxt.t_base, rr_nxt);
             if (tr_on) GTRACE(0, tr_i, 1);
             tc_wait_ld();
             if (tr_on) GTRACE(0, tr_i, 2);
@@ -633,16 +748,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     epilogue_chunk_coalesced(p.epi, g_cur, stage_buf, lane, cur.b, cur.t_base, p.T,
                                              cur.n0c, v, rr_cur, p.dbg);
-                } else if constexpr (EPI == 2) {
+                } else if constexpr (pair) {
                     float v[64];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]), v[32 + j] = __uint_as_float(r2[j]);
-                    epilogue_item_tma<true>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                    if constexpr (direct) epilogue_item_direct<true>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                    else epilogue_item_tma<true>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
                 } else {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    epilogue_item_tma<false>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                    if constexpr (direct) epilogue_item_direct<false>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                    else epilogue_item_tma<false>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
                 }
             }
             if (tr_on) GTRACE(0, tr_i, 3);
@@ -782,7 +899,7 @@ bool encode_bf16_map(CUtensorMap* map, const void* ptr, int K, long long rows, l
 
 // (N_out, T, B) view of an output tensor for the TMA-store epilogue: box {32, 32, 1}, no swizzle
 static bool encode_out_map(CUtensorMap* map, const void* ptr, bool f32, int n_out, long long rows,
-                           long long rstride, long long batches, long long bstride) {
+                           long long rstride, long long batches, long long bstride, bool swizzled) {
     EncodeTiledFn fn = get_encode_fn();
     const int es = f32 ? 4 : 2;
     if (fn == nullptr || ptr == nullptr) return false;
@@ -796,8 +913,8 @@ static bool encode_out_map(CUtensorMap* map, const void* ptr, bool f32, int n_ou
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    !swizzled ? CU_TENSOR_MAP_SWIZZLE_NONE : f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
@@ -822,9 +939,11 @@ static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
     const bool pair = p.epi.act == SVC_ACT_SWIGLU_PAIR || p.epi.act == SVC_ACT_TANH_SIG_PAIR;
     if (p.store_mode == 0) return launch_tc_epi<BN, STAGES, 0>(p, m_tiles, stream);
     if constexpr (BN >= 64) {
-        if (pair) return launch_tc_epi<BN, STAGES, 2>(p, m_tiles, stream);
+        if (pair) return p.direct ? launch_tc_epi<BN, STAGES, 4>(p, m_tiles, stream)
+                                  : launch_tc_epi<BN, STAGES, 2>(p, m_tiles, stream);
     }
-    return launch_tc_epi<BN, STAGES, 1>(p, m_tiles, stream);
+    return p.direct ? launch_tc_epi<BN, STAGES, 3>(p, m_tiles, stream)
+                    : launch_tc_epi<BN, STAGES, 1>(p, m_tiles, stream);
 }
 
 static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
@@ -898,19 +1017,24 @@ static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
     p.epi = make_epi_params(d);
     // ---- TMA-store epilogue when the output pattern allows it ------------------------------
     static const int no_tma_store = getenv("SVC_NO_TMA_STORE") ? 1 : 0;
+    static const int no_direct = getenv("SVC_NO_DIRECT") ? 1 : 0;
     p.store_mode = 0;
+    // row-layout epilogue (no transpose); RoPE needs the pair-major table
+    p.direct = !no_direct && d.N % 4 == 0 &&
+               (d.act != SVC_ACT_ROPE || (d.rope_tab_t != nullptr && d.rope_ld > 0 &&
+                                          reinterpret_cast<uintptr_t>(d.rope_tab_t) % 8 == 0));
     if (p.epi.vec_ok && !no_tma_store) {
         const bool res_inplace = d.res != nullptr && d.res == d.out_f32 && d.res_bstride == d.of_bstride &&
                                  d.res_rstride == d.of_rstride;
         if (d.out_op != nullptr && d.out_f32 == nullptr && d.res == nullptr && !d.accumulate) {
-            if (encode_out_map(&p.omap, d.out_op, false, p.epi.N_out, d.T, d.oo_rstride, d.B, d.oo_bstride))
+            if (encode_out_map(&p.omap, d.out_op, false, p.epi.N_out, d.T, d.oo_rstride, d.B, d.oo_bstride, p.direct))
                 p.store_mode = 1;
         } else if (d.out_f32 != nullptr && d.out_op == nullptr && d.act != SVC_ACT_ROPE) {
             const bool add = (res_inplace && !d.accumulate && d.alpha == 1.0f) ||
                              (d.res == nullptr && d.accumulate);
             const bool plain = d.res == nullptr && !d.accumulate;
             if ((add || plain) &&
-                encode_out_map(&p.omap, d.out_f32, true, p.epi.N_out, d.T, d.of_rstride, d.B, d.of_bstride))
+                encode_out_map(&p.omap, d.out_f32, true, p.epi.N_out, d.T, d.of_rstride, d.B, d.of_bstride, p.direct))
                 p.store_mode = add ? 2 : 3;
         }
     }

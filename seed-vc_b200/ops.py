@@ -33,6 +33,7 @@ class Ops:
         self.backend = BACKEND_SIMT if force_simt else BACKEND_AUTO
         self.precise = 1 if mode == "fp32" else 0
         self.launches = 0
+        self._rope_t = {}        # rope table data_ptr -> (table, pair-major copy)
         self.profile = None      # list of [category, flops, bytes, start_event, end_event] when on
 
     # ------------------------------------------------------------------ optional per-launch timing
@@ -125,6 +126,11 @@ class Ops:
             assert act == ACT_ROPE and tab.dtype == torch.float32 and tab.is_contiguous()
             assert tab.shape[0] >= pos0 + T and tab.shape[1:] == (32, 2)
             d.rope_tab, d.rope_cols, d.rope_pos0 = tab.data_ptr(), rope_cols, pos0
+            tt = self._rope_t.get(tab.data_ptr())
+            if tt is None or tt[0] is not tab:      # pair-major copy for the row-layout epilogue
+                tt = (tab, tab.permute(1, 0, 2).contiguous())
+                self._rope_t[tab.data_ptr()] = tt
+            d.rope_tab_t, d.rope_ld = tt[1].data_ptr(), tab.shape[0]
             d.q_cols, d.q_scale = q_cols, q_scale
         if gate is not None:
             assert gate.dtype == torch.float32 and gate.shape == (B, n_out) and gate.stride(1) == 1

@@ -40,7 +40,7 @@ def test_binding_covers_header():
 
 def test_load_library_and_version(lib):
     l = _lib.load_library()
-    assert l.svc_version() == 100
+    assert l.svc_version() == 101
     assert l.svc_last_error() is not None
 
 
