@@ -41,6 +41,9 @@ struct alignas(64) TcParams {
     // 2 = fp32 tile reduce-added into out_f32 (in-place residual), 3 = fp32 tile -> out_f32
     int store_mode;
     int direct;                // 1: row-layout epilogue writes the swizzled TMA tile directly (no transpose)
+    int res_rows;              // direct: residual read in the row layout (one 128 B line per thread)
+    int dual;                  // direct: fp32 tile -> out_f32 (omap) AND bf16 tile -> out_op (omap2)
+    CUtensorMap omap2;
     CUtensorMap omap;          // (N_out, T, B) view of the output, box {32, 32, 1}; swizzled when direct
     EpiParams epi;
 };
@@ -59,13 +62,14 @@ constexpr int kEpiWarps = 8;             // two epilogue groups of 4 warps (one 
 constexpr int kTcThreads = 64 + kEpiWarps * 32;    // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kStageRowF = 32;           // fp32 row of the per-warp transpose buffer (XOR-swizzled)
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPW = 4096>
 struct TcSmem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int EPI_BYTES = kEpiWarps * 32 * kStageRowF * 4;
+    static constexpr int EPI_WARP_BYTES = EPW;       // per epilogue warp: fp32 tile (+ bf16 tile when dual)
+    static constexpr int EPI_BYTES = kEpiWarps * EPW;
     static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
     static_assert(TOTAL <= 232448, "shared memory budget");
@@ -447,6 +451,20 @@ __device__ __forceinline__ void rope_prefetch_rows(const EpiParams& e, int c0, i
     }
 }
 
+// residual values of this lane's row for a 32-column item (its own 128 B line; the eight requests of
+// a warp touch the same 32 lines, so seven of them hit L1)
+__device__ __forceinline__ void res_prefetch_rows(const EpiParams& e, int c0, int lane, int b, int t_base,
+                                                  int T, float4 (&rr)[8]) {
+    const int t = t_base + lane;
+    if (t < T) {
+        const float* rp = e.res + static_cast<long long>(b) * e.res_bstride +
+                          static_cast<long long>(t) * e.res_rstride + c0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (c0 + 4 * q < e.N_out) rr[q] = *reinterpret_cast<const float4*>(rp + 4 * q);
+    }
+}
+
 // Direct TMA-store epilogue: the whole item is finished in the TMEM row layout (thread = output row,
 // 32 consecutive output columns in registers; per-column operands are warp-uniform loads) and written
 // once into a swizzled shared-memory tile that the TMA store reads (bf16: 64B rows, SWIZZLE_64B; fp32:
@@ -507,6 +525,11 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
                 v[j] *= q.x, v[j + 1] *= q.y, v[j + 2] *= q.z, v[j + 3] *= q.w;
             }
     }
+    if (!PAIR && p.res_rows) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            v[4 * q] += rr[q].x, v[4 * q + 1] += rr[q].y, v[4 * q + 2] += rr[q].z, v[4 * q + 3] += rr[q].w;
+    }
     if (e.alpha != 1.0f) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
@@ -515,15 +538,16 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     if (lane == 0) bulk_wait_read0();
     __syncwarp();
     uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
-    if (p.store_mode == 1) {
-        uint8_t* row = sb + lane * 64;
+    if (p.store_mode == 1 || p.dual) {
+        uint8_t* row = sb + (p.dual ? 4096 : 0) + lane * 64;
         const int sw = (lane >> 1) & 3;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             *reinterpret_cast<uint4*>(row + ((q ^ sw) << 4)) =
                 make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
                            pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
-    } else {
+    }
+    if (p.store_mode != 1) {
         uint8_t* row = sb + lane * 128;
         const int sw = lane & 7;
 #pragma unroll
@@ -536,6 +560,7 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     if (lane == 0) {
         if (p.store_mode == 2) tma_reduce_add_3d(&p.omap, stage, c0, t_base, b);
         else tma_store_3d(&p.omap, stage, c0, t_base, b);
+        if (p.dual) tma_store_3d(&p.omap2, sb + 4096, c0, t_base, b);
         bulk_commit();
     }
 }
@@ -548,7 +573,7 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
 // registers and code small.
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
-    using S = TcSmem<BN, STAGES>;
+    using S = TcSmem<BN, STAGES, EPI == 5 ? 6144 : 4096>;
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -665,11 +690,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         const int ew = warp - 2;
         const int group = ew >> 2;
         const int lg = warp & 3;             // TMEM lane group this warp may access
-        float* stage_buf = reinterpret_cast<float*>(smem + S::EPI_OFFSET) + ew * 32 * kStageRowF;
+        float* stage_buf = reinterpret_cast<float*>(smem + S::EPI_OFFSET + ew * S::EPI_WARP_BYTES);
         const uint32_t taddr = tmem_base + group * ACC_COLS + (static_cast<uint32_t>(lg * 32) << 16);
         constexpr bool tma_mode = EPI != 0;
         constexpr bool pair = EPI == 2 || EPI == 4;
-        constexpr bool direct = EPI >= 3;
+        constexpr bool direct = EPI >= 3;          // 3 direct, 4 direct pair, 5 direct with two outputs
         constexpr int acc_per_item = pair ? 64 : 32;   // accumulator columns per work item
         struct Item {
             int it, ch, b, t_base, n0c, ncols;
@@ -715,6 +740,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             epi_prefetch(p.epi, g_cur, lane, cur.b, cur.t_base, p.T, rr_cur);
         if (rope_direct && cur.valid && cur.n0c < p.epi.rope_cols)
             rope_prefetch_rows(p.epi, cur.n0c, lane, cur.t_base, rr_cur);
+        const bool res_direct = direct && !pair && p.res_rows;
+        if (res_direct && cur.valid) res_prefetch_rows(p.epi, cur.n0c, lane, cur.b, cur.t_base, p.T, rr_cur);
         int tr_i = 0;
         const bool tr_on = (warp == 2 && lane == 0);
         while (cur.valid) {
@@ -733,6 +760,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 epi_prefetch(p.epi, g_nxt, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
             if (rope_direct && nxt.valid && nxt.n0c < p.epi.rope_cols)
                 rope_prefetch_rows(p.epi, nxt.n0c, lane, nxt.t_base, rr_nxt);
+            if (res_direct && nxt.valid) res_prefetch_rows(p.epi, nxt.n0c, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
             if (tr_on) GTRACE(0, tr_i, 1);
             tc_wait_ld();
             if (tr_on) GTRACE(0, tr_i, 2);
@@ -920,7 +948,7 @@ static bool encode_out_map(CUtensorMap* map, const void* ptr, bool f32, int n_ou
 
 template <int BN, int STAGES, int EPI>
 static int launch_tc_epi(const TcParams& p, int m_tiles, cudaStream_t stream) {
-    using S = TcSmem<BN, STAGES>;
+    using S = TcSmem<BN, STAGES, EPI == 5 ? 6144 : 4096>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI>,
@@ -942,6 +970,7 @@ static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
         if (pair) return p.direct ? launch_tc_epi<BN, STAGES, 4>(p, m_tiles, stream)
                                   : launch_tc_epi<BN, STAGES, 2>(p, m_tiles, stream);
     }
+    if (p.dual) return launch_tc_epi<BN, (BN == 256 ? 3 : STAGES - 1), 5>(p, m_tiles, stream);
     return p.direct ? launch_tc_epi<BN, STAGES, 3>(p, m_tiles, stream)
                     : launch_tc_epi<BN, STAGES, 1>(p, m_tiles, stream);
 }
@@ -1038,7 +1067,21 @@ static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
                 p.store_mode = add ? 2 : 3;
         }
     }
-    if (BN < 64 && (d.act == SVC_ACT_SWIGLU_PAIR || d.act == SVC_ACT_TANH_SIG_PAIR)) p.store_mode = 0;
+    // two outputs (fp32 stream + bf16 operand copy), optionally with a residual read in the row layout
+    const bool pair_act = d.act == SVC_ACT_SWIGLU_PAIR || d.act == SVC_ACT_TANH_SIG_PAIR;
+    if (p.store_mode == 0 && p.direct && p.epi.vec_ok && !no_tma_store && !pair_act &&
+        d.act != SVC_ACT_ROPE && d.out_f32 != nullptr && !(d.accumulate && d.out_op != nullptr) &&
+        d.out_op != nullptr) {   // (row-layout residual reads without a second output measured slower than EPI 0)
+        bool ok = encode_out_map(&p.omap, d.out_f32, true, p.epi.N_out, d.T, d.of_rstride, d.B, d.of_bstride, true);
+        if (ok && d.out_op != nullptr)
+            ok = encode_out_map(&p.omap2, d.out_op, false, p.epi.N_out, d.T, d.oo_rstride, d.B, d.oo_bstride, true);
+        if (ok) {
+            p.store_mode = d.accumulate ? 2 : 3;
+            p.res_rows = d.res != nullptr;
+            p.dual = d.out_op != nullptr;
+        }
+    }
+    if (BN < 64 && pair_act) p.store_mode = 0;
     const int m_tiles = d.B * p.tiles_per_batch;
     switch (BN) {
         case 32: return launch_tc<32, 8>(p, m_tiles, stream);
