@@ -250,50 +250,86 @@ __global__ void __launch_bounds__(256) snake_aa2_kernel(const TI* __restrict__ x
     }
 }
 
+constexpr int kPostTL = 128;    // output samples per block of snake_conv_post_kernel
+
 // activation_post + conv_post (C -> 1, k taps, zero padding) + clamp / tanh.
 // Reference: modules/bigvgan/bigvgan.py:377-384.
+// One block = TL output samples.  Four phases through shared memory so every upsampled Snake value
+// (6 FMA + 1 sin) is computed once: x tile -> u (2x rate) -> y (down FIR) -> conv over k taps x C.
+// Threads are (row = tid / 32, channel = tid % 32): no integer division by the runtime C.
 template <bool PRECISE>
 __global__ void __launch_bounds__(256) snake_conv_post_kernel(
     const float* __restrict__ x, const float* __restrict__ a_p, const float* __restrict__ invb_p,
     const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out, int L, int C,
     int ksize, int use_tanh) {
-    constexpr int TL = 256;
+    constexpr int TL = kPostTL;
     extern __shared__ float sm[];
     const int half = ksize / 2;
-    const int xr = TL + 2 * half + 10;        // x rows staged
-    const int yr = TL + 2 * half;             // activation rows needed
-    float* xs = sm;                           // xr * (C+1)
-    float* ys = xs + xr * (C + 1);            // yr * (C+1)
-    float* ws = ys + yr * (C + 1);            // ksize * C
+    const int CS = C + 1;                     // odd row stride: conflict-free column walks
+    const int YR = TL + 2 * half;             // activation rows needed by the conv
+    const int UR = 2 * YR + 10;               // upsampled rows needed by the down FIR
+    const int XR = YR + 13;                   // x rows needed by the up FIR
+    float* xs = sm;                           // XR * CS
+    float* us = xs + XR * CS;                 // UR * CS
+    float* ys = us + UR * CS;                 // YR * CS
+    float* ws = ys + YR * CS;                 // ksize * C
     const int b = blockIdx.y;
     const int l0 = blockIdx.x * TL;
+    const int lbase = l0 - half - 6;          // x row 0
+    const int m0 = 2 * (l0 - half) - 5;       // u row 0
+    const int tc = threadIdx.x & 31, tr = threadIdx.x >> 5;
+    const bool interior = lbase >= 0 && lbase + XR <= L;
     const float* xb = x + static_cast<long long>(b) * L * C;
-    for (int i = threadIdx.x; i < xr * C; i += 256) {
-        const int r = i / C, c = i % C;
-        const int l = min(max(l0 - half - 5 + r, 0), L - 1);
-        xs[r * (C + 1) + c] = xb[static_cast<long long>(l) * C + c];
+    for (int r = tr; r < XR; r += 8) {
+        const int l = min(max(lbase + r, 0), L - 1);
+        for (int c = tc; c < C; c += 32) xs[r * CS + c] = xb[static_cast<long long>(l) * C + c];
     }
     for (int i = threadIdx.x; i < ksize * C; i += 256) ws[i] = w[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < yr * C; i += 256) {
-        const int r = i / C, c = i % C;
-        const int n = l0 - half + r;
-        float y = 0.f;
-        if (n >= 0 && n < L) {
-            const float a = a_p[c], inv_b = invb_p[c];
-            auto xat = [&](int l) { return xs[(l - (l0 - half - 5)) * (C + 1) + c]; };
+    for (int c = tc; c < C; c += 32) {
+        const float a = a_p[c], inv_b = invb_p[c];
+        for (int i = tr; i < UR; i += 8) {
+            const int m = min(max(m0 + i, 0), 2 * L - 1);
+            const int q = m >> 1;
+            // odd m: taps h[0,2,..] on x[q+3-j]; even m: taps h[1,3,..] on x[q+2-j]  (j = 0..5)
+            const int odd = m & 1;
+            const float* xp = xs + (q + 2 + odd - lbase) * CS + c;
+            float acc = 0.f;
+            if (interior) {                   // no sequence end inside this block: taps are in range
 #pragma unroll
-            for (int k = 0; k < 12; ++k)
-                y = fmaf(c_h12[k], up_point<PRECISE>(2 * n + k - 5, L, a, inv_b, xat), y);
+                for (int j = 0; j < 6; ++j) acc = fmaf(odd ? c_h12[2 * j] : c_h12[2 * j + 1], xp[-j * CS], acc);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int l = min(max(q + 2 + odd - j, 0), L - 1) - (q + 2 + odd);   // clamp at the ends
+                    acc = fmaf(odd ? c_h12[2 * j] : c_h12[2 * j + 1], xp[l * CS], acc);
+                }
+            }
+            us[i * CS + c] = snake_fn<PRECISE>(2.0f * acc, a, inv_b);
         }
-        ys[r * (C + 1) + c] = y;
+    }
+    __syncthreads();
+    for (int c = tc; c < C; c += 32) {
+        for (int r = tr; r < YR; r += 8) {
+            const int n = l0 - half + r;
+            float y = 0.f;
+            if (n >= 0 && n < L) {
+                const float* up = us + (2 * r) * CS + c;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) y = fmaf(c_h12[k], up[k * CS], y);
+            }
+            ys[r * CS + c] = y;
+        }
     }
     __syncthreads();
     const int n = l0 + threadIdx.x;
-    if (n < L) {
+    if (threadIdx.x < TL && n < L) {
         float acc = bias != nullptr ? bias[0] : 0.f;
-        for (int k = 0; k < ksize; ++k)
-            for (int c = 0; c < C; ++c) acc = fmaf(ws[k * C + c], ys[(threadIdx.x + k) * (C + 1) + c], acc);
+        for (int k = 0; k < ksize; ++k) {
+            const float* yp = ys + (threadIdx.x + k) * CS;
+            const float* wp = ws + k * C;
+            for (int c = 0; c < C; ++c) acc = fmaf(wp[c], yp[c], acc);
+        }
         acc = use_tanh ? tanhf(acc) : fminf(fmaxf(acc, -1.0f), 1.0f);
         out[static_cast<long long>(b) * L + n] = acc;
     }
@@ -378,8 +414,13 @@ extern "C" int svc_snake_conv_post(const float* x, const float* a, const float* 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int half = ksize / 2;
-    const int smem = ((256 + 2 * half + 10) + (256 + 2 * half)) * (C + 1) * 4 + ksize * C * 4;
-    dim3 grid((L + 255) / 256, B);
+    const int yr = kPostTL + 2 * half;
+    const int smem = ((yr + 13) + (2 * yr + 10) + yr) * (C + 1) * 4 + ksize * C * 4;
+    if (smem > 200 * 1024) {
+        svc_set_error("svc_snake_conv_post: C * ksize too large for the shared-memory tile");
+        return SVC_ERR_ARG;
+    }
+    dim3 grid((L + kPostTL - 1) / kPostTL, B);
     if (precise) {
         cudaFuncSetAttribute(snake_conv_post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         snake_conv_post_kernel<true><<<grid, 256, smem, st>>>(x, a, inv_b, w, bias, out, L, C, ksize, use_tanh);
