@@ -229,65 +229,60 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         }
     } else if (warp >= 1 && warp <= AT_QT) {
         reg_dealloc<40>();
-        if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
-            const uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_HD, 0, 1);   // B (=V) MN-major
-            // descriptor lo words of the smem regions (address field only varies)
-            const uint32_t q_lo0 = desc_lo(smem_u32(smem + S::Q_OFF));
-            const uint32_t k_lo0 = desc_lo(smem_u32(smem + S::K_OFF));
-            const uint32_t v_lo0 = desc_lo(smem_u32(smem + S::V_OFF), 1024);   // MN-major: LBO = 1024
-            auto issue_s = [&](int g, int j) {
-                const int st = j % AT_KST;
-                if (g == 0) TRACE(0, j, 2);
-                if (g == 1) TRACE(3, j, 3);
-                tc_fence_after();
-                const uint32_t qlo = q_lo0 + g * (S::QTILE >> 4);
+        // MMA issuer of Q tile g = warp - 1.  The whole warp runs this loop (uniform control flow, all
+        // operands warp-uniform) and only the tcgen05 instructions sit under elect_one(): ptxas then
+        // keeps descriptors in uniform registers.  Issuing from a divergent `if (lane == 0)` region
+        // cost an elect / 5 x R2UR / branch sequence per MMA (~110 cycles each, measured), which made
+        // this thread the pacing resource of the tile's S -> softmax -> PV chain.
+        const int g = warp - 1;
+        const uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
+        const uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_HD, 0, 1);   // B (=V) MN-major
+        // descriptor lo words of the smem regions (address field only varies)
+        const uint32_t qlo = desc_lo(smem_u32(smem + S::Q_OFF)) + g * (S::QTILE >> 4);
+        const uint32_t k_lo0 = desc_lo(smem_u32(smem + S::K_OFF));
+        const uint32_t v_lo0 = desc_lo(smem_u32(smem + S::V_OFF), 1024);   // MN-major: LBO = 1024
+        const uint32_t tS = tmem_S + g * AT_BN, tO = tmem_O + g * AT_HD, tP = tmem_P + g * (AT_BN / 2);
+        auto issue_s = [&](int st) {
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t klo = k_lo0 + st * (S::KTILE >> 4);
 #pragma unroll
                 for (int k = 0; k < AT_HD / 16; ++k)
-                    tc_mma_f16_lh(tmem_S + g * AT_BN, qlo + k * 2, kDescHiSw128, klo + k * 2, kDescHiSw128,
-                                  idesc_s, k != 0);
+                    tc_mma_f16_lh(tS, qlo + k * 2, kDescHiSw128, klo + k * 2, kDescHiSw128, idesc_s, k != 0);
                 tc_commit(&s_full[g]);
-                if (g == 1) TRACE(3, j, 4);
-            };
-            auto issue_pv = [&](int g, int j) {
-                const int st = j % AT_KST;
-                if (g == 0) TRACE(0, j, 5);
-                if (g == 1) TRACE(3, j, 0);
-                tc_fence_after();
-                if (g == 1) TRACE(3, j, 1);
+                tc_commit(&k_empty[st]);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int st, bool first) {
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t vlo = v_lo0 + st * (S::KTILE >> 4);
 #pragma unroll
                 for (int k = 0; k < AT_BN / 16; ++k)      // A = P from TMEM: 8 columns per 16 keys
-                    tc_mma_f16_ts(tmem_O + g * AT_HD, tmem_P + g * (AT_BN / 2) + k * 8,
-                                  vlo + k * (2048 >> 4), kDescHiSw128, idesc_o, (j | k) != 0);
-                if (g == 1) TRACE(3, j, 2);
+                    tc_mma_f16_ts(tO, tP + k * 8, vlo + k * (2048 >> 4), kDescHiSw128, idesc_o,
+                                  (k != 0 || !first) ? 1u : 0u);
                 tc_commit(&p_empty[g]);
-                if (g == AT_QT - 1) TRACE(0, j, 6);
-            };
-            mbar_wait(q_full, 0);
-            // One issuing thread per softmax group (warp 1 -> group 0, warp 2 -> group 1): the
-            // groups run independent S / PV chains, so neither waits behind the other's barriers
-            // or its ~75-cycle-per-MMA issue time.  K / V stages are released when both have
-            // committed (k_empty / v_empty count 2).
-            const int g = warp - 1;
-            mbar_wait(&k_full[0], 0);
-            issue_s(g, 0);
-            tc_commit(&k_empty[0]);
-            for (int j = 0; j < n_blocks; ++j) {
-                if (j + 1 < n_blocks) {
-                    const int st = (j + 1) % AT_KST;
-                    mbar_wait(&k_full[st], ((j + 1) / AT_KST) & 1);
-                    mbar_wait(&s_empty[g], ((j + 1) & 1) ^ 1);      // softmax g has S_g(j) in registers
-                    issue_s(g, j + 1);
-                    tc_commit(&k_empty[st]);
-                }
-                const int st = j % AT_KST;
-                mbar_wait(&v_full[st], (j / AT_KST) & 1);
-                mbar_wait(&p_full[g], j & 1);
-                issue_pv(g, j);
                 tc_commit(&v_empty[st]);
             }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&k_full[0], 0);
+        issue_s(0);
+        int st_n = 1, ph_n = 0;          // ring stage / phase of block j + 1
+        int st_c = 0, ph_c = 0;          // ring stage / phase of block j
+        for (int j = 0; j < n_blocks; ++j) {
+            if (j + 1 < n_blocks) {
+                mbar_wait(&k_full[st_n], ph_n);
+                mbar_wait(&s_empty[g], j & 1);          // softmax g has S_g(j) in registers
+                issue_s(st_n);
+                if (++st_n == AT_KST) st_n = 0, ph_n ^= 1;
+            }
+            mbar_wait(&v_full[st_c], ph_c);
+            mbar_wait(&p_full[g], j & 1);
+            issue_pv(st_c, j == 0);
+            if (++st_c == AT_KST) st_c = 0, ph_c ^= 1;
         }
     } else if (warp < 4) {
         reg_dealloc<40>();
