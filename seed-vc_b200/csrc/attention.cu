@@ -267,20 +267,20 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             }
             __syncwarp();
         };
-        mbar_wait(q_full, 0);
-        mbar_wait(&k_full[0], 0);
+        mbar_wait_warp(q_full, 0);
+        mbar_wait_warp(&k_full[0], 0);
         issue_s(0);
         int st_n = 1, ph_n = 0;          // ring stage / phase of block j + 1
         int st_c = 0, ph_c = 0;          // ring stage / phase of block j
         for (int j = 0; j < n_blocks; ++j) {
             if (j + 1 < n_blocks) {
-                mbar_wait(&k_full[st_n], ph_n);
-                mbar_wait(&s_empty[g], j & 1);          // softmax g has S_g(j) in registers
+                mbar_wait_warp(&k_full[st_n], ph_n);
+                mbar_wait_warp(&s_empty[g], j & 1);          // softmax g has S_g(j) in registers
                 issue_s(st_n);
                 if (++st_n == AT_KST) st_n = 0, ph_n ^= 1;
             }
-            mbar_wait(&v_full[st_c], ph_c);
-            mbar_wait(&p_full[g], j & 1);
+            mbar_wait_warp(&v_full[st_c], ph_c);
+            mbar_wait_warp(&p_full[g], j & 1);
             issue_pv(st_c, j == 0);
             if (++st_c == AT_KST) st_c = 0, ph_c ^= 1;
         }
