@@ -180,6 +180,17 @@ int svc_timestep_embedding(const float* t, const float* freqs, float* out, int n
 int svc_set_rows(const float* src, long long src_bstride, float* dst, long long dst_bstride, int B,
                  int D, void* stream);
 
+/* Stitch n vocoded chunks into one waveform (inference.py:343-350 `crossfade`, :505-527 chunk loop;
+ * seed_vc_wrapper.py:190-285 `_stream_wave_chunks`).  waves is (n, wave_stride) fp32, chunk k holds
+ * lens[k] samples.  Chunks k < n-1 contribute samples [0, lens[k]-overlap), the last one all of its
+ * samples; out offset of chunk k is offs[k] (offs[0] = 0, offs[k+1] = offs[k] + lens[k] - overlap).
+ * For k > 0 the first `overlap` samples are w_k[i]*fade_in[i] + w_{k-1}[lens[k-1]-overlap+i]*fade_out[i],
+ * evaluated in fp64 and rounded to fp32 once (numpy float32*float64 semantics of the reference);
+ * fade_in / fade_out are the reference's cos^2 ramps (fp64, `overlap` entries, device memory). */
+int svc_crossfade_stitch(const float* waves, long long wave_stride, const int* lens, const long long* offs,
+                         int n_chunks, int overlap, const double* fade_in, const double* fade_out,
+                         float* out, long long total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

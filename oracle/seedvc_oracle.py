@@ -22,6 +22,8 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
+
 import torch
 import torch.nn.functional as F
 
@@ -403,3 +405,55 @@ def _wn_weight_convT(sd, prefix):
     """ConvTranspose1d weight (I, O, k): weight_norm dim=0 is per *input* channel
     (SURVEY section 8 a16)."""
     return _wn_weight(sd, prefix)
+
+
+# ---------------------------------------------------------------------------------------------
+# Long-form chunk loop (SURVEY 8f N1)
+# ---------------------------------------------------------------------------------------------
+def crossfade(chunk1, chunk2, overlap):
+    """inference.py:343-350 / seed_vc_wrapper.py:190-199 (numpy; chunk2 is modified in place)."""
+    fade_out = np.cos(np.linspace(0, np.pi / 2, overlap)) ** 2
+    fade_in = np.cos(np.linspace(np.pi / 2, 0, overlap)) ** 2
+    if len(chunk2) < overlap:
+        chunk2[:overlap] = chunk2[:overlap] * fade_in[:len(chunk2)] + (chunk1[-overlap:] * fade_out)[:len(chunk2)]
+    else:
+        chunk2[:overlap] = chunk2[:overlap] * fade_in + chunk1[-overlap:] * fade_out
+    return chunk2
+
+
+def chunk_plan(n_source_frames, n_prompt_frames, max_context_window, overlap_frame_len=16):
+    """(start, length, is_last) of every window the reference loop visits (inference.py:470-476 and the
+    ``processed_frames += vc_target.size(2) - overlap_frame_len`` updates at :512,:516,:522)."""
+    window = max_context_window - n_prompt_frames
+    plan, processed = [], 0
+    while processed < n_source_frames:
+        length = min(window, n_source_frames - processed)
+        is_last = processed + window >= n_source_frames
+        plan.append((processed, length, is_last))
+        if is_last:
+            break
+        processed += length - overlap_frame_len
+    return plan
+
+
+def stitch_chunks(waves, overlap_wave_len):
+    """waves: list of 1-D float32 arrays, one per window in loop order -> concatenated output
+    (inference.py:505-527; seed_vc_wrapper.py:227-285 with stream_output=False)."""
+    out, previous = [], None
+    n = len(waves)
+    for k, w in enumerate(waves):
+        w = np.array(w, dtype=np.float32, copy=True)
+        is_last = k == n - 1
+        if k == 0:
+            if is_last:
+                out.append(w)
+                break
+            out.append(w[:-overlap_wave_len])
+            previous = w[-overlap_wave_len:]
+        elif is_last:
+            out.append(crossfade(previous, w, overlap_wave_len))
+        else:
+            out.append(crossfade(previous, w[:-overlap_wave_len], overlap_wave_len))
+            previous = w[-overlap_wave_len:]
+    return np.concatenate(out)
+

@@ -361,6 +361,49 @@ extern "C" int svc_set_rows(const float* src, long long src_bstride, float* dst,
 }
 
 // ------------------------------------------------------------------------------------------
+// Overlap / cos^2 crossfade stitching of vocoded chunks (inference.py:343-350,505-527;
+// seed_vc_wrapper.py:190-285): every chunk but the last drops its final `ov` samples, every chunk
+// but the first blends its first `ov` samples with the previous chunk's dropped tail.  The blend is
+// done in fp64 and rounded to fp32 once, exactly as numpy does for float32 * float64 arrays.
+// ------------------------------------------------------------------------------------------
+__global__ void crossfade_stitch_kernel(const float* __restrict__ waves, long long wstride,
+                                        const int* __restrict__ lens, const long long* __restrict__ offs,
+                                        int n, int ov, const double* __restrict__ fade_in,
+                                        const double* __restrict__ fade_out, float* __restrict__ out,
+                                        long long total) {
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        int k = 0;
+        while (k + 1 < n && idx >= offs[k + 1]) ++k;
+        const long long i = idx - offs[k];
+        float v = waves[k * wstride + i];
+        if (k > 0 && i < ov) {
+            const float t = waves[(k - 1) * wstride + lens[k - 1] - ov + i];
+            v = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(v), fade_in[i]),
+                                             __dmul_rn(static_cast<double>(t), fade_out[i])));
+        }
+        out[idx] = v;
+    }
+}
+
+extern "C" int svc_crossfade_stitch(const float* waves, long long wave_stride, const int* lens,
+                                    const long long* offs, int n_chunks, int overlap,
+                                    const double* fade_in, const double* fade_out, float* out,
+                                    long long total, void* stream) {
+    if (n_chunks < 1 || overlap < 0 || total < 0 || waves == nullptr || lens == nullptr || offs == nullptr ||
+        out == nullptr || (overlap > 0 && n_chunks > 1 && (fade_in == nullptr || fade_out == nullptr))) {
+        svc_set_error("svc_crossfade_stitch: bad arguments");
+        return SVC_ERR_ARG;
+    }
+    if (total == 0) return SVC_OK;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 16));
+    crossfade_stitch_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        waves, wave_stride, lens, offs, n_chunks, overlap, fade_in, fade_out, out, total);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // error plumbing shared by all translation units
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";

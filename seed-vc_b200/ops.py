@@ -296,3 +296,35 @@ class Ops:
         check(self.lib.svc_set_rows(src.data_ptr(), sb, dst.data_ptr(), dst.stride(0), B, D,
                                     self._stream()), "svc_set_rows")
         self._t1()
+
+    def crossfade_stitch(self, waves, lens, overlap):
+        """Stitch vocoded chunks (n, Lmax) fp32 with per-chunk sample counts ``lens`` into one
+        waveform; cos^2 crossfade over ``overlap`` samples.  Reference: inference.py:343-350,505-527."""
+        import numpy as np
+        self._chk(waves)
+        n = waves.shape[0]
+        assert waves.dtype == torch.float32 and waves.stride(1) == 1 and len(lens) == n
+        lens = [int(v) for v in lens]
+        assert all(0 < v <= waves.shape[1] for v in lens)
+        if n > 1:
+            assert all(v >= overlap for v in lens[:-1]), "only the last chunk may be shorter than the overlap"
+        offs = [0]
+        for k in range(n - 1):
+            offs.append(offs[-1] + lens[k] - overlap)
+        total = offs[-1] + lens[-1]
+        dev = waves.device
+        # the reference's ramps, fp64 (inference.py:344-345)
+        fo = np.cos(np.linspace(0, np.pi / 2, overlap)) ** 2
+        fi = np.cos(np.linspace(np.pi / 2, 0, overlap)) ** 2
+        fo_d = torch.from_numpy(fo).to(dev)
+        fi_d = torch.from_numpy(fi).to(dev)
+        lens_d = torch.tensor(lens, dtype=torch.int32, device=dev)
+        offs_d = torch.tensor(offs, dtype=torch.int64, device=dev)
+        out = torch.empty(total, dtype=torch.float32, device=dev)
+        self._t0("misc")
+        check(self.lib.svc_crossfade_stitch(waves.data_ptr(), waves.stride(0), lens_d.data_ptr(),
+                                            offs_d.data_ptr(), n, overlap, fi_d.data_ptr(), fo_d.data_ptr(),
+                                            out.data_ptr(), total, self._stream()), "svc_crossfade_stitch")
+        self._t1()
+        return out
+

@@ -172,3 +172,42 @@ def test_inference_api_and_cpu_refusal():
     cpu = CFM(configs.scaled_down(configs.v1_model_params("xlsr_tiny")))
     with pytest.raises(RuntimeError):
         cpu.inference(mu.cpu(), torch.tensor([60, 60]), prompt.cpu(), style.cpu(), None, 2)
+
+
+def test_long_form_chunks_match_sequential_loop():
+    """one batched ragged conversion + GPU stitching == the reference's sequential
+    window loop (run here with the same CUDA modules per window, stitched by the oracle)."""
+    import seedvc_oracle as orc
+    from seedvc_b200.chunking import chunk_plan, convert_chunks
+
+    cfm, args = v1_model("whisper_small", True, "fp32")
+    if "voc" not in _models:
+        _models["voc"] = BigVGAN(configs.bigvgan_h()).to(DEV)
+    voc = _models["voc"]
+    voc.set_mode("fp32")
+    S, Tp, mcw, hop, steps, cfg = 150, 24, 84, 256, 2, 0.7
+    D = args.DiT.content_dim
+    g = torch.Generator().manual_seed(4)
+    cond = torch.randn(1, S, D, generator=g).to(DEV)
+    prompt_cond = torch.randn(1, Tp, D, generator=g).to(DEV)
+    mel2 = (torch.randn(1, 80, Tp, generator=g) * 2 - 4).to(DEV)
+    style2 = torch.randn(1, 192, generator=g).to(DEV)
+    plan = chunk_plan(S, Tp, mcw)
+    assert len(plan) == 4 and plan[-1][1] < plan[0][1]
+    Tmax = Tp + plan[0][1]
+    z = torch.randn(len(plan), 80, Tmax, generator=g).to(DEV)
+    wave = convert_chunks(cfm, voc, cond, prompt_cond, mel2, style2, steps, cfg, mcw, hop=hop, z=z)
+    # the reference's loop: one window at a time
+    t_span = torch.linspace(0, 1, steps + 1, device=DEV)
+    waves = []
+    for k, (start, length, _) in enumerate(plan):
+        cat = torch.cat([prompt_cond, cond[:, start:start + length]], dim=1)
+        T = Tp + length
+        mel = cfm.solve_euler(z[k:k + 1, :, :T].clone(), torch.tensor([T], device=DEV), mel2, cat, style2,
+                              None, t_span, cfg)
+        waves.append(voc(mel[:, :, Tp:].contiguous())[0, 0].cpu().numpy())
+    want = orc.stitch_chunks(waves, 16 * hop)
+    assert wave.shape == (1, want.shape[0])
+    e = rel_l2(wave[0].cpu(), torch.from_numpy(want))
+    print(f"long-form {len(plan)} windows vs sequential loop [fp32] rel-L2 {e:.2e}")
+    assert e < 1e-3

@@ -111,3 +111,20 @@ def test_bigvgan_loads_weight_norm_checkpoint():
     sd["conv_pre.weight_v"], sd["conv_pre.weight_g"] = v * 3.0, g
     voc.load_state_dict(sd)
     assert torch.allclose(voc.conv_pre.weight, v * 1.5, atol=1e-6)
+
+
+def test_chunk_plan_matches_reference_loop():
+    """Host chunk scheduler (seed-vc_b200/chunking.py) vs the windows the REAL reference loop visited."""
+    import json
+    import os
+
+    import numpy as np
+    from seedvc_b200.chunking import chunk_plan
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "stitch_kat.npz"))
+    for name, m in json.loads(str(z["meta"])).items():
+        plan = chunk_plan(m["S"], m["Tp"], m["max_context_window"], m["overlap_frame_len"])
+        assert [list(p) for p in plan] == [list(p) for p in m["plan"]], name
+    import pytest
+    with pytest.raises(ValueError):
+        chunk_plan(100, 70, 80, 16)

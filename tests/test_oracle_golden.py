@@ -72,3 +72,24 @@ def test_bigvgan_matches_reference(name, manifest):
     mel = synth.synth_mel(m["B"], h.num_mels, m["Tm"])
     wav = orc.bigvgan_forward(sd, h, mel)
     assert rel_l2(wav, g["wav"]) < TOL
+
+
+def test_chunk_loop_against_reference_golden():
+    """oracle.stitch_chunks / chunk_plan vs the REAL reference methods (oracle/gen_golden_chunks.py)."""
+    import json
+    import os
+
+    import numpy as np
+    import seedvc_oracle as orc
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "stitch_kat.npz"))
+    meta = json.loads(str(z["meta"]))
+    for name, m in meta.items():
+        plan = orc.chunk_plan(m["S"], m["Tp"], m["max_context_window"], m["overlap_frame_len"])
+        assert [list(p) for p in plan] == [list(p) for p in m["plan"]], name
+        waves = [z[f"{name}_w{k}"] for k in range(len(plan))]
+        got = orc.stitch_chunks(waves, m["overlap_frame_len"] * m["hop"])
+        assert got.dtype == np.float32 and got.shape == z[name + "_out"].shape
+        assert np.array_equal(got, z[name + "_out"]), name      # bit-exact
+    short = orc.crossfade(z["xf_c1"].copy(), z["xf_c2"].copy(), 64)
+    assert np.array_equal(short, z["xf_out"])
