@@ -180,6 +180,25 @@ int svc_timestep_embedding(const float* t, const float* freqs, float* out, int n
 int svc_set_rows(const float* src, long long src_bstride, float* dst, long long dst_bstride, int B,
                  int D, void* stream);
 
+/* ---- InterpolateRegulator pieces (modules/length_regulator.py:90-141) ----------------------------
+ * svc_interp_rows: out[b,t,:] = src[b, idx[t], :] (+ add_vec[:]) (+ emb[emb_q[b*q_bstride + emb_idx[t]], :])
+ *   = F.interpolate(x, size, mode='nearest') as a row gather (:115; idx is the caller's nearest-index
+ *   table), `x + f0_mask` (:122) or `x + interpolate(f0_embedding(quantized_f0))` (:124-129).
+ *   src fp32 (B, Tin, D); out (B, Tout, D) fp32 or bf16 (dtype). */
+int svc_interp_rows(const float* src, long long src_bstride, long long src_rstride, const int* idx,
+                    const float* add_vec, const float* emb, const int* emb_q, long long q_bstride,
+                    const int* emb_idx, void* out, long long out_bstride, long long out_rstride, int B,
+                    int Tout, int D, int dtype, void* stream);
+/* svc_groupnorm1_mish: out = Mish(GroupNorm(1 group, C)(x)) for x (B, T, C) fp32 frames-major: mean / var
+ *   over all T*C values of a sample (fp64 accumulation), per-channel affine, Mish = y*tanh(softplus(y))
+ *   (nn.GroupNorm(groups=1) + nn.Mish, :50-53).  stats_ws: 2*B doubles of scratch. */
+int svc_groupnorm1_mish(const float* x, long long bstride, long long rstride, const float* gamma,
+                        const float* beta, float eps, double* stats_ws, void* out, long long out_bstride,
+                        long long out_rstride, int B, int T, int C, int dtype, int precise, void* stream);
+/* svc_mask_rows: x[b, t, :] = 0 for t >= lens[b]  (`out * mask`, :140). */
+int svc_mask_rows(float* x, long long bstride, long long rstride, const int* lens, int B, int T, int D,
+                  void* stream);
+
 /* Stitch n vocoded chunks into one waveform (inference.py:343-350 `crossfade`, :505-527 chunk loop;
  * seed_vc_wrapper.py:190-285 `_stream_wave_chunks`).  waves is (n, wave_stride) fp32, chunk k holds
  * lens[k] samples.  Chunks k < n-1 contribute samples [0, lens[k]-overlap), the last one all of its

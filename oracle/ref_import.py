@@ -48,6 +48,18 @@ def _install_stubs():
         mpl.pylab, mpl.pyplot = pylab, pyplot
         sys.modules.update({"matplotlib": mpl, "matplotlib.pylab": pylab,
                             "matplotlib.pyplot": pyplot})
+    if "dac" not in sys.modules:      # modules/length_regulator.py:7 imports the (unused here) VQ layer
+        dac = types.ModuleType("dac")
+        dnn = types.ModuleType("dac.nn")
+        dq = types.ModuleType("dac.nn.quantize")
+
+        class VectorQuantize:           # never instantiated: the v1 presets set vector_quantize: false
+            def __init__(self, *a, **k):
+                raise RuntimeError("dac is not installed")
+
+        dq.VectorQuantize = VectorQuantize
+        dac.nn, dnn.quantize = dnn, dq
+        sys.modules.update({"dac": dac, "dac.nn": dnn, "dac.nn.quantize": dq})
     if "librosa" not in sys.modules:
         lb = types.ModuleType("librosa")
         util = types.ModuleType("librosa.util")
@@ -79,10 +91,11 @@ def load():
     from modules.v2.cfm import CFM as CFMv2  # noqa: E402
     from modules.v2.dit_wrapper import DiT as DiTv2  # noqa: E402
     from modules.wavenet import WN  # noqa: E402
+    from modules.length_regulator import InterpolateRegulator  # noqa: E402
 
     ns = types.SimpleNamespace(
         CFM=CFM, DiT=DiT, BigVGAN=BigVGAN, BigVGANAttrDict=BigVGANAttrDict,
         Activation1d=Activation1d, SnakeBeta=SnakeBeta, Snake=Snake,
-        CFMv2=CFMv2, DiTv2=DiTv2, WN=WN,
+        CFMv2=CFMv2, DiTv2=DiTv2, WN=WN, InterpolateRegulator=InterpolateRegulator,
     )
     return ns

@@ -457,3 +457,45 @@ def stitch_chunks(waves, overlap_wave_len):
             previous = w[-overlap_wave_len:]
     return np.concatenate(out)
 
+
+# ---------------------------------------------------------------------------------------------
+# InterpolateRegulator - modules/length_regulator.py:90-141, continuous / non-VQ branch
+# ---------------------------------------------------------------------------------------------
+def _f0_to_coarse(f0, f0_bin):
+    """modules/length_regulator.py:9-26."""
+    f0_mel_min = 1127 * np.log(1 + 50.0 / 700)
+    f0_mel_max = 1127 * np.log(1 + 1100.0 / 700)
+    f0_mel = 1127 * (1 + f0 / 700).log()
+    a = (f0_bin - 2) / (f0_mel_max - f0_mel_min)
+    b = f0_mel_min * a - 1.
+    f0_mel = torch.where(f0_mel > 0, f0_mel * a - b, f0_mel)
+    c = torch.round(f0_mel).long()
+    c = c * (c > 0)
+    c = c + ((c < 1) * 1)
+    c = c * (c < f0_bin)
+    c = c + ((c >= f0_bin) * (f0_bin - 1))
+    return c
+
+
+def interpolate_regulator(sd, x, ylens, n_blocks=4, f0=None, f0_condition=False, n_f0_bins=512):
+    """sd: reference state_dict of InterpolateRegulator; x (B, Tin, in_channels); ylens (B,) long.
+    Returns ``out * mask`` (B, max(ylens), out_channels) - length_regulator.py:112-141."""
+    x = F.linear(x.float(), sd["content_in_proj.weight"], sd["content_in_proj.bias"])          # :111
+    Tout = int(ylens.max())
+    mask = (torch.arange(Tout)[None, :] < ylens[:, None]).unsqueeze(-1)                         # :113
+    x = F.interpolate(x.transpose(1, 2).contiguous(), size=Tout, mode="nearest")               # :115
+    if f0_condition:
+        if f0 is None:
+            x = x + sd["f0_mask"].unsqueeze(-1)                                                 # :122
+        else:
+            q = _f0_to_coarse(f0, n_f0_bins).clamp(0, n_f0_bins - 1).long()                     # :125-126
+            e = F.embedding(q, sd["f0_embedding.weight"])
+            x = x + F.interpolate(e.transpose(1, 2).contiguous(), size=Tout, mode="nearest")    # :127-129
+    for i in range(n_blocks):                                                                   # :47-53
+        x = F.conv1d(x, sd[f"model.{3 * i}.weight"], sd[f"model.{3 * i}.bias"], padding=1)
+        x = F.group_norm(x, 1, sd[f"model.{3 * i + 1}.weight"], sd[f"model.{3 * i + 1}.bias"], 1e-5)
+        x = F.mish(x)
+    k = 3 * n_blocks
+    x = F.conv1d(x, sd[f"model.{k}.weight"], sd[f"model.{k}.bias"])                             # :55-57
+    return x.transpose(1, 2).contiguous() * mask                                                # :131,140
+

@@ -57,6 +57,11 @@ SIGNATURES = {
     "svc_reflect_halo": [c_vp, c_ll, c_ll, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp],
     "svc_timestep_embedding": [c_vp, c_vp, c_vp, c_int, c_int, c_vp],
     "svc_set_rows": [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_vp],
+    "svc_interp_rows": [c_vp, c_ll, c_ll, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp, c_ll, c_ll, c_int, c_int,
+                        c_int, c_int, c_vp],
+    "svc_groupnorm1_mish": [c_vp, c_ll, c_ll, c_vp, c_vp, c_float, c_vp, c_vp, c_ll, c_ll, c_int, c_int, c_int,
+                            c_int, c_int, c_vp],
+    "svc_mask_rows": [c_vp, c_ll, c_ll, c_vp, c_int, c_int, c_int, c_vp],
     "svc_crossfade_stitch": [c_vp, c_ll, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_ll, c_vp],
 }
 

@@ -361,6 +361,164 @@ extern "C" int svc_set_rows(const float* src, long long src_bstride, float* dst,
 }
 
 // ------------------------------------------------------------------------------------------
+// InterpolateRegulator pieces (modules/length_regulator.py:90-141)
+// ------------------------------------------------------------------------------------------
+// out[b, t, :] = src[b, idx[t], :] (+ add_vec) (+ emb[q[b, eidx[t]], :])  -- F.interpolate(mode='nearest')
+// as a row gather (:115), `x + f0_mask` (:122) or `x + interpolate(f0_embedding(quantized_f0))` (:125-129)
+template <typename TO>
+__global__ void __launch_bounds__(128) interp_rows_kernel(
+    const float* __restrict__ src, long long sb, long long sr, const int* __restrict__ idx,
+    const float* __restrict__ add_vec, const float* __restrict__ emb, const int* __restrict__ q,
+    long long qb, const int* __restrict__ eidx, TO* __restrict__ out, long long ob, long long orow, int D) {
+    const int t = blockIdx.x, b = blockIdx.y;
+    const float* s = src + b * sb + static_cast<long long>(idx[t]) * sr;
+    const float* e = emb != nullptr ? emb + static_cast<long long>(q[b * qb + eidx[t]]) * D : nullptr;
+    TO* o = out + b * ob + static_cast<long long>(t) * orow;
+    for (int c = threadIdx.x; c < D; c += 128) {
+        float v = s[c];
+        if (add_vec != nullptr) v += add_vec[c];
+        if (e != nullptr) v += e[c];
+        o[c] = from_f32<TO>(v);
+    }
+}
+
+// GroupNorm(1 group) statistics of one sample = all T*C values (nn.GroupNorm(1, C), :51): fp64 sums
+__global__ void __launch_bounds__(256) gn1_stats_kernel(const float* __restrict__ x, long long bstride,
+                                                        long long rstride, int T, int C,
+                                                        double* __restrict__ stats) {
+    const int b = blockIdx.y;
+    const float* xb = x + b * bstride;
+    double s = 0.0, ss = 0.0;
+    const long long n = static_cast<long long>(T) * C;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+        const int t = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<long long>(t) * C);
+        const double v = xb[static_cast<long long>(t) * rstride + c];
+        s += v;
+        ss += v * v;
+    }
+    __shared__ double sh[2][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        ss += __shfl_down_sync(0xffffffffu, ss, o);
+    }
+    if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s, sh[1][threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c2 = 0.0;
+        for (int w = 0; w < 8; ++w) a += sh[0][w], c2 += sh[1][w];
+        atomicAdd(&stats[2 * b], a);
+        atomicAdd(&stats[2 * b + 1], c2);
+    }
+}
+
+// y = Mish((x - mean) * rstd * gamma[c] + beta[c]); Mish(y) = y * tanh(softplus(y)) (nn.Mish, :52)
+template <typename TO, bool PRECISE>
+__global__ void __launch_bounds__(256) gn1_mish_kernel(const float* __restrict__ x, long long bstride,
+                                                       long long rstride, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps,
+                                                       const double* __restrict__ stats, TO* __restrict__ out,
+                                                       long long ob, long long orow, int T, int C) {
+    const int b = blockIdx.y;
+    const double n = static_cast<double>(T) * C;
+    const double mean_d = stats[2 * b] / n;
+    const double var_d = fmax(stats[2 * b + 1] / n - mean_d * mean_d, 0.0);
+    const float mean = static_cast<float>(mean_d);
+    const float rstd = static_cast<float>(1.0 / sqrt(var_d + static_cast<double>(eps)));
+    const long long total = static_cast<long long>(T) * C;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+        const int t = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<long long>(t) * C);
+        const float v = x[b * bstride + static_cast<long long>(t) * rstride + c];
+        const float y = (v - mean) * rstd * gamma[c] + beta[c];
+        const float sp = y > 20.0f ? y : (PRECISE ? log1pf(expf(y)) : __logf(1.0f + __expf(y)));
+        const float m = y * (PRECISE ? tanhf(sp) : tanhf(sp));
+        out[b * ob + static_cast<long long>(t) * orow + c] = from_f32<TO>(m);
+    }
+}
+
+// x[b, t, :] = 0 for t >= lens[b]   (`out * mask`, :140)
+__global__ void __launch_bounds__(128) mask_rows_kernel(float* __restrict__ x, long long bstride,
+                                                        long long rstride, const int* __restrict__ lens,
+                                                        int D) {
+    const int t = blockIdx.x, b = blockIdx.y;
+    if (t < lens[b]) return;
+    float* o = x + b * bstride + static_cast<long long>(t) * rstride;
+    for (int c = threadIdx.x; c < D; c += 128) o[c] = 0.f;
+}
+
+extern "C" int svc_interp_rows(const float* src, long long src_bstride, long long src_rstride,
+                               const int* idx, const float* add_vec, const float* emb, const int* emb_q,
+                               long long q_bstride, const int* emb_idx, void* out, long long out_bstride,
+                               long long out_rstride, int B, int Tout, int D, int dtype, void* stream) {
+    if (B < 1 || Tout < 1 || D < 1 || src == nullptr || idx == nullptr || out == nullptr ||
+        (emb != nullptr && (emb_q == nullptr || emb_idx == nullptr))) {
+        svc_set_error("svc_interp_rows: bad arguments");
+        return SVC_ERR_ARG;
+    }
+    dim3 grid(Tout, B);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == SVC_F32)
+        interp_rows_kernel<float><<<grid, 128, 0, st>>>(src, src_bstride, src_rstride, idx, add_vec, emb,
+                                                        emb_q, q_bstride, emb_idx, static_cast<float*>(out),
+                                                        out_bstride, out_rstride, D);
+    else
+        interp_rows_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(
+            src, src_bstride, src_rstride, idx, add_vec, emb, emb_q, q_bstride, emb_idx,
+            static_cast<__nv_bfloat16*>(out), out_bstride, out_rstride, D);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_groupnorm1_mish(const float* x, long long bstride, long long rstride, const float* gamma,
+                                   const float* beta, float eps, double* stats_ws, void* out,
+                                   long long out_bstride, long long out_rstride, int B, int T, int C,
+                                   int dtype, int precise, void* stream) {
+    if (B < 1 || T < 1 || C < 1 || x == nullptr || gamma == nullptr || beta == nullptr ||
+        stats_ws == nullptr || out == nullptr) {
+        svc_set_error("svc_groupnorm1_mish: bad arguments");
+        return SVC_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * B, st);
+    const long long n = static_cast<long long>(T) * C;
+    const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 592));
+    dim3 grid(blocks, B);
+    gn1_stats_kernel<<<grid, 256, 0, st>>>(x, bstride, rstride, T, C, stats_ws);
+    if (dtype == SVC_F32) {
+        if (precise)
+            gn1_mish_kernel<float, true><<<grid, 256, 0, st>>>(x, bstride, rstride, gamma, beta, eps, stats_ws,
+                                                              static_cast<float*>(out), out_bstride,
+                                                              out_rstride, T, C);
+        else
+            gn1_mish_kernel<float, false><<<grid, 256, 0, st>>>(x, bstride, rstride, gamma, beta, eps, stats_ws,
+                                                               static_cast<float*>(out), out_bstride,
+                                                               out_rstride, T, C);
+    } else {
+        if (precise)
+            gn1_mish_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(
+                x, bstride, rstride, gamma, beta, eps, stats_ws, static_cast<__nv_bfloat16*>(out), out_bstride,
+                out_rstride, T, C);
+        else
+            gn1_mish_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(
+                x, bstride, rstride, gamma, beta, eps, stats_ws, static_cast<__nv_bfloat16*>(out), out_bstride,
+                out_rstride, T, C);
+    }
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_mask_rows(float* x, long long bstride, long long rstride, const int* lens, int B, int T,
+                             int D, void* stream) {
+    if (B < 1 || T < 1 || D < 1 || x == nullptr || lens == nullptr) {
+        svc_set_error("svc_mask_rows: bad arguments");
+        return SVC_ERR_ARG;
+    }
+    mask_rows_kernel<<<dim3(T, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(x, bstride, rstride, lens, D);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // Overlap / cos^2 crossfade stitching of vocoded chunks (inference.py:343-350,505-527;
 // seed_vc_wrapper.py:190-285): every chunk but the last drops its final `ov` samples, every chunk
 // but the first blends its first `ov` samples with the previous chunk's dropped tail.  The blend is

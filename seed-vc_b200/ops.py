@@ -328,3 +328,44 @@ class Ops:
         self._t1()
         return out
 
+    # ------------------------------------------------------------------ length regulator pieces
+    def interp_rows(self, src, idx, out, add_vec=None, emb=None, emb_q=None, emb_idx=None):
+        """out[b,t,:] = src[b,idx[t],:] (+ add_vec) (+ emb[emb_q[b, emb_idx[t]]]); length_regulator.py:115-129."""
+        self._chk(src, idx, out, add_vec, emb, emb_q, emb_idx)
+        B, Tout, D = out.shape
+        assert src.dtype == torch.float32 and src.stride(2) == 1 and out.stride(2) == 1 and src.shape[2] == D
+        assert idx.dtype == torch.int32 and idx.numel() == Tout
+        self._t0("misc")
+        check(self.lib.svc_interp_rows(
+            src.data_ptr(), src.stride(0), src.stride(1), idx.data_ptr(),
+            add_vec.data_ptr() if add_vec is not None else None,
+            emb.data_ptr() if emb is not None else None,
+            emb_q.data_ptr() if emb_q is not None else None,
+            emb_q.stride(0) if emb_q is not None else 0,
+            emb_idx.data_ptr() if emb_idx is not None else None,
+            out.data_ptr(), out.stride(0), out.stride(1), B, Tout, D, self._code(out.dtype),
+            self._stream()), "svc_interp_rows")
+        self._t1()
+
+    def groupnorm1_mish(self, x, gamma, beta, out, eps=1e-5):
+        """out = Mish(GroupNorm(1, C)(x)), x (B, T, C) fp32; length_regulator.py:50-53."""
+        self._chk(x, gamma, beta, out)
+        B, T, Cc = x.shape
+        assert x.dtype == torch.float32 and x.stride(2) == 1 and out.stride(2) == 1 and out.shape == x.shape
+        ws = torch.empty(2 * B, dtype=torch.float64, device=x.device)
+        self._t0("misc")
+        check(self.lib.svc_groupnorm1_mish(x.data_ptr(), x.stride(0), x.stride(1), gamma.data_ptr(),
+                                           beta.data_ptr(), eps, ws.data_ptr(), out.data_ptr(), out.stride(0),
+                                           out.stride(1), B, T, Cc, self._code(out.dtype), self.precise,
+                                           self._stream()), "svc_groupnorm1_mish")
+        self._t1()
+
+    def mask_rows(self, x, lens):
+        self._chk(x, lens)
+        B, T, D = x.shape
+        assert x.dtype == torch.float32 and x.stride(2) == 1 and lens.dtype == torch.int32
+        self._t0("misc")
+        check(self.lib.svc_mask_rows(x.data_ptr(), x.stride(0), x.stride(1), lens.data_ptr(), B, T, D,
+                                     self._stream()), "svc_mask_rows")
+        self._t1()
+

@@ -211,3 +211,28 @@ def test_long_form_chunks_match_sequential_loop():
     e = rel_l2(wave[0].cpu(), torch.from_numpy(want))
     print(f"long-form {len(plan)} windows vs sequential loop [fp32] rel-L2 {e:.2e}")
     assert e < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_length_regulator_golden(mode):
+    """InterpolateRegulator on the CUDA kernels vs the REAL reference module's outputs."""
+    import json
+    import os
+
+    import numpy as np
+    import gen_golden_lr as gl
+    from seedvc_b200.length_regulator import InterpolateRegulator
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "length_regulator.npz"))
+    for name, m in json.loads(str(z["meta"])).items():
+        lr = InterpolateRegulator(**m["kw"], mode=mode)
+        sd = synth.synth_state_dict({"length_regulator." + k: v for k, v in m["keys"].items()})
+        missing = lr.load_state_dict({k[len("length_regulator."):]: v for k, v in sd.items()}, strict=True)
+        lr = lr.to(DEV)
+        x, f0 = gl.inputs(name, m["B"], m["Tin"], m["kw"]["in_channels"], Tf0=m["Tin"] + 3 if m["f0"] else None)
+        y, olens, *_ = lr(x.to(DEV), ylens=torch.tensor(m["ylens"], device=DEV), n_quantizers=3,
+                          f0=None if f0 is None else f0.to(DEV))
+        e = rel_l2(y.cpu(), z[name])
+        print(f"length regulator {name} [{mode}] rel-L2 {e:.2e}")
+        assert tuple(y.shape) == z[name].shape and e < TOL[mode]
+        assert [int(v) for v in olens] == m["ylens"]

@@ -128,3 +128,17 @@ def test_chunk_plan_matches_reference_loop():
     import pytest
     with pytest.raises(ValueError):
         chunk_plan(100, 70, 80, 16)
+
+
+def test_nearest_index_matches_aten():
+    """Host nearest-neighbour index table (length_regulator.nearest_index) vs F.interpolate(mode='nearest')."""
+    import torch
+    import torch.nn.functional as F
+    from seedvc_b200.length_regulator import nearest_index
+
+    for n_in, n_out in [(60, 103), (47, 81), (40, 80), (50, 86), (1500, 2580), (2580, 1500), (7, 7), (3, 1000),
+                        (999, 1000), (1000, 999), (1293, 2227)]:
+        src = torch.arange(n_in, dtype=torch.float32).view(1, 1, n_in)
+        want = F.interpolate(src, size=n_out, mode="nearest").view(-1).long().numpy()
+        got = nearest_index(n_in, n_out)
+        assert (got == want).all(), (n_in, n_out)

@@ -93,3 +93,29 @@ def test_chunk_loop_against_reference_golden():
         assert np.array_equal(got, z[name + "_out"]), name      # bit-exact
     short = orc.crossfade(z["xf_c1"].copy(), z["xf_c2"].copy(), 64)
     assert np.array_equal(short, z["xf_out"])
+
+
+def test_length_regulator_oracle_against_reference_golden():
+    """oracle.interpolate_regulator vs outputs of the REAL InterpolateRegulator (oracle/gen_golden_lr.py)."""
+    import json
+    import os
+
+    import numpy as np
+    import torch
+    import gen_golden_lr as gl
+    import seedvc_oracle as orc
+    from seedvc_b200 import synth
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "length_regulator.npz"))
+    meta = json.loads(str(z["meta"]))
+    for name, m in meta.items():
+        sd = synth.synth_state_dict({"length_regulator." + k: v for k, v in m["keys"].items()})
+        sd = {k[len("length_regulator."):]: v for k, v in sd.items()}
+        x, f0 = gl.inputs(name, m["B"], m["Tin"], m["kw"]["in_channels"], Tf0=m["Tin"] + 3 if m["f0"] else None)
+        y = orc.interpolate_regulator(sd, x, torch.tensor(m["ylens"]), f0=f0,
+                                      f0_condition=m["kw"].get("f0_condition", False),
+                                      n_f0_bins=m["kw"].get("n_f0_bins", 512))
+        want = torch.from_numpy(z[name])
+        assert y.shape == want.shape
+        e = float((y - want).norm() / want.norm())
+        assert e < 1e-5, (name, e)
