@@ -259,8 +259,12 @@ class BASECFM(nn.Module):
         return self.solve_euler(z, x_lens, prompt, mu, style, f0, t_span, inference_cfg_rate)
 
     @torch.no_grad()
-    def solve_euler(self, x, x_lens, prompt, mu, style, f0, t_span, inference_cfg_rate=0.5):
+    def solve_euler(self, x, x_lens, prompt, mu, style, f0, t_span, inference_cfg_rate=0.5, *,
+                    t_values_dev=None):
         """Fixed-step Euler with batched CFG.  Reference: modules/flow_matching.py:55-112.
+
+        ``t_values_dev`` (keyword only, used by graphs.GraphedConversion): the per-step times already on
+        the device, so that no host-to-device copy happens inside a CUDA-graph capture.
 
         x: (B, C, T) noise; prompt: (B, C, Tp); mu: (B, T, content_dim); style: (B, 192);
         ``f0`` is accepted and ignored like in the reference (App. D-3)."""
@@ -296,7 +300,8 @@ class BASECFM(nn.Module):
         prompt_op = ops.zeros(B, T, C, device=dev)
         if Tp > 0:
             ops.bct_to_btc(prompt[..., :Tp].float().contiguous(), prompt_op[:, :Tp, :])
-        st = eng.begin(branches, prompt_op, mu.float(), style.float(), x_lens, torch.stack(t_vals))
+        st = eng.begin(branches, prompt_op, mu.float(), style.float(), x_lens,
+                       torch.stack(t_vals) if t_values_dev is None else t_values_dev)
         for s in range(len(dts)):
             v = eng.step(s, x_op)
             ops.cfg_euler(xs, v, coefs, dts[s], Tp, st["x_lens"], x_op)

@@ -236,3 +236,26 @@ def test_length_regulator_golden(mode):
         print(f"length regulator {name} [{mode}] rel-L2 {e:.2e}")
         assert tuple(y.shape) == z[name].shape and e < TOL[mode]
         assert [int(v) for v in olens] == m["ylens"]
+
+
+def test_cuda_graph_replay_equals_eager():
+    """graphs.GraphedConversion: one captured graph launch == the eager launch sequence, bit for bit,
+    also after the inputs change."""
+    from seedvc_b200.graphs import GraphedConversion
+
+    cfm, args = v1_model("xlsr_tiny", True, "bf16")
+    if "voc" not in _models:
+        _models["voc"] = BigVGAN(configs.bigvgan_h()).to(DEV)
+    voc = _models["voc"]
+    voc.set_mode("bf16")
+    B, T, Tp, steps, cfg = 1, 90, 30, 3, 0.7
+    g = GraphedConversion(cfm, voc, B, T, Tp, steps, cfg)
+    t_span = torch.linspace(0, 1, steps + 1, device=DEV)
+    for first in (0, 5):
+        mu, prompt, style, z = [t.to(DEV) for t in synth.synth_batch(B, T, Tp, 80, args.DiT.content_dim,
+                                                                     first_id=first)]
+        lens = torch.tensor([T], device=DEV)
+        got = g(mu, lens, prompt, style, z).clone()
+        mel = cfm.solve_euler(z.clone(), lens, prompt, mu, style, None, t_span, cfg)
+        want = voc(mel[:, :, Tp:].contiguous())
+        assert torch.equal(got, want)
