@@ -34,6 +34,7 @@ class Ops:
         self.precise = 1 if mode == "fp32" else 0
         self.launches = 0
         self._rope_t = {}        # rope table data_ptr -> (table, pair-major copy)
+        self.use_rope_t = True   # False: pass only the position-major table (exercises the fallback epilogue)
         self.profile = None      # list of [category, flops, bytes, start_event, end_event] when on
 
     # ------------------------------------------------------------------ optional per-launch timing
@@ -130,7 +131,8 @@ class Ops:
             if tt is None or tt[0] is not tab:      # pair-major copy for the row-layout epilogue
                 tt = (tab, tab.permute(1, 0, 2).contiguous())
                 self._rope_t[tab.data_ptr()] = tt
-            d.rope_tab_t, d.rope_ld = tt[1].data_ptr(), tab.shape[0]
+            if self.use_rope_t:
+                d.rope_tab_t, d.rope_ld = tt[1].data_ptr(), tab.shape[0]
             d.q_cols, d.q_scale = q_cols, q_scale
         if gate is not None:
             assert gate.dtype == torch.float32 and gate.shape == (B, n_out) and gate.stride(1) == 1

@@ -37,8 +37,9 @@ def ops_for(mode, simt=False):
 
 def run_gemm_case(mode, simt, B, T, N, Ks, shifts=None, rows=None, bias=False, rowbias=False,
                   act=0, gate=False, res=False, alpha=1.0, accumulate=False, both_out=False,
-                  rope=False, seed=0, share_a=False):
+                  rope=False, seed=0, share_a=False, out_kind=None, inplace=False, legacy_rope=False):
     ops, emu = ops_for(mode, simt), EmuOps()
+    ops.use_rope_t = not legacy_rope
     od = ops.op_dtype
     shifts = shifts or [0] * len(Ks)
     rows = rows or T
@@ -68,19 +69,26 @@ def run_gemm_case(mode, simt, B, T, N, Ks, shifts=None, rows=None, bias=False, r
         kw["rope"] = (rope_table(T + 3).to(DEV), 2 * (N // 3), 2, N // 3, 0.125)
         act = 4
     init = rnd(B, T, n_out, seed=seed + 104)
-    out_f32 = init.clone()
+    out_kind = out_kind or ("both" if both_out else "f32")
+    out_f32 = init.clone() if out_kind in ("f32", "both") else None
     out_ref = init.clone()
-    out_op = torch.zeros(B, T, n_out, dtype=od, device=DEV) if both_out else None
-    out_op_ref = torch.zeros(B, T, n_out, device=DEV) if both_out else None
+    if inplace:                      # h += f(A) with the residual read from the output buffer itself
+        kw["res"] = out_f32
+    kw_ref = dict(kw)
+    if inplace:
+        kw_ref["res"] = init.clone()
+    out_op = torch.zeros(B, T, n_out, dtype=od, device=DEV) if out_kind in ("op", "both") else None
+    out_op_ref = torch.zeros(B, T, n_out, device=DEV) if out_op is not None else None
     ops.gemm(segs, N, B=B, T=T, act=act, alpha=alpha, accumulate=accumulate, out_f32=out_f32,
              out_op=out_op, **kw)
     emu.gemm(segs_ref, N, B=B, T=T, act=act, alpha=alpha, accumulate=accumulate, out_f32=out_ref,
-             out_op=out_op_ref, **kw)
+             out_op=out_op_ref, **kw_ref)
     torch.cuda.synchronize()
     tol = 1e-5 if mode == "fp32" else 2e-4
-    e = rel_l2(out_f32, out_ref)
-    assert e < tol, f"out_f32 rel-L2 {e}"
-    if both_out:
+    if out_f32 is not None:
+        e = rel_l2(out_f32, out_ref)
+        assert e < tol, f"out_f32 rel-L2 {e}"
+    if out_op is not None:
         e2 = rel_l2(out_op.float(), out_ref)
         assert e2 < (1e-5 if mode == "fp32" else 4e-3), f"out_op rel-L2 {e2}"
 
@@ -119,6 +127,29 @@ def test_gemm_epilogues(mode, simt):
     run_gemm_case(mode, simt, 2, 150, 256, [128], bias=True, res=True, alpha=1 / 3,
                   accumulate=True, both_out=True)
     run_gemm_case(mode, simt, 2, 150, 384, [128], rope=True, both_out=True)
+
+
+@pytest.mark.parametrize("mode,simt", [("bf16", False), ("fp32", False)])
+def test_gemm_store_paths(mode, simt):
+    """Every output pattern the tensor-core path specialises: operand-only tile stores (plain, SiLU,
+    SwiGLU / gate pairs, RoPE with and without the pair-major table), fp32-only stores (plain, in-place
+    residual as a TMA reduce-add, accumulate-only, separate residual), two outputs, ragged N."""
+    for N, K in ((256, 128), (80, 128), (24, 64)):
+        run_gemm_case(mode, simt, 2, 150, N, [K], bias=True, out_kind="op")
+        run_gemm_case(mode, simt, 2, 150, N, [K], bias=True, out_kind="f32")
+        run_gemm_case(mode, simt, 2, 150, N, [K], bias=True, inplace=True, out_kind="f32")
+        run_gemm_case(mode, simt, 2, 150, N, [K], accumulate=True, out_kind="f32")
+        run_gemm_case(mode, simt, 2, 150, N, [K], bias=True, res=True, alpha=0.5, out_kind="f32")
+        run_gemm_case(mode, simt, 2, 150, N, [K], bias=True, inplace=True, out_kind="both")
+        run_gemm_case(mode, simt, 2, 150, N, [K], rowbias=True, out_kind="both")
+    run_gemm_case(mode, simt, 2, 150, 256, [128], bias=True, act=1, out_kind="op")               # SiLU
+    run_gemm_case(mode, simt, 3, 200, 512, [128], act=2, out_kind="op")                          # SwiGLU
+    run_gemm_case(mode, simt, 2, 150, 512, [128], rowbias=True, act=3, out_kind="op")            # gate
+    run_gemm_case(mode, simt, 2, 150, 160, [128], act=2, out_kind="op")                          # ragged pair
+    run_gemm_case(mode, simt, 2, 150, 256, [128], gate=True, inplace=True, out_kind="f32")       # v2 gate
+    run_gemm_case(mode, simt, 2, 333, 384, [128], rope=True, out_kind="op")                      # direct RoPE
+    run_gemm_case(mode, simt, 2, 333, 384, [128], rope=True, out_kind="op", legacy_rope=True)    # fallback
+    run_gemm_case(mode, simt, 2, 333, 1536, [512], rope=True, out_kind="op")
 
 
 @pytest.mark.parametrize("mode,simt", [("bf16", False), ("fp32", False)])
