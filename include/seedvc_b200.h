@@ -199,6 +199,18 @@ int svc_groupnorm1_mish(const float* x, long long bstride, long long rstride, co
 int svc_mask_rows(float* x, long long bstride, long long rstride, const int* lens, int B, int T, int D,
                   void* stream);
 
+/* ---- mel front-end pieces (modules/audio.py:45-82 `mel_spectrogram`) --------------------------------
+ * The STFT is svc_gemm (fp32) over the padded audio viewed as rows of `hop` samples, n_fft/hop segments with
+ * row shifts 0..n_fft/hop-1, against the Hann-windowed DFT matrix [cos | -sin].
+ * svc_reflect_pad1d: out[b, i] = y[b, reflect(i - pad)], i < L + 2*pad; zeros up to out_len (:58-61). */
+int svc_reflect_pad1d(const float* y, long long y_bstride, int B, int L, int pad, float* out,
+                      long long out_bstride, long long out_len, void* stream);
+/* svc_stft_mag: mag[m,k] = sqrt(re^2 + im^2 + eps), spec row m = [re_0..re_{nb-1} | im_0..im_{nb-1} | pad] (:78) */
+int svc_stft_mag(const float* spec, long long spec_rstride, long long rows, int n_bins, float eps, float* mag,
+                 long long mag_rstride, void* stream);
+/* svc_log_clamp: x = log(max(x, clip))  (dynamic_range_compression_torch, :24-25) */
+int svc_log_clamp(float* x, long long n, float clip, void* stream);
+
 /* Stitch n vocoded chunks into one waveform (inference.py:343-350 `crossfade`, :505-527 chunk loop;
  * seed_vc_wrapper.py:190-285 `_stream_wave_chunks`).  waves is (n, wave_stride) fp32, chunk k holds
  * lens[k] samples.  Chunks k < n-1 contribute samples [0, lens[k]-overlap), the last one all of its

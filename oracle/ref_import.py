@@ -65,7 +65,11 @@ def _install_stubs():
         util = types.ModuleType("librosa.util")
         util.normalize = lambda x, *a, **k: x
         filters = types.ModuleType("librosa.filters")
-        filters.mel = lambda *a, **k: None
+        def _mel(*a, **k):      # modules/audio.py:4 - librosa itself is absent: the oracle's restatement
+            import seedvc_oracle
+            return seedvc_oracle.slaney_mel_filterbank(*a, **k)
+
+        filters.mel = _mel
         lb.util, lb.filters = util, filters
         sys.modules.update({"librosa": lb, "librosa.util": util,
                             "librosa.filters": filters})
@@ -92,10 +96,11 @@ def load():
     from modules.v2.dit_wrapper import DiT as DiTv2  # noqa: E402
     from modules.wavenet import WN  # noqa: E402
     from modules.length_regulator import InterpolateRegulator  # noqa: E402
+    from modules.audio import mel_spectrogram  # noqa: E402
 
     ns = types.SimpleNamespace(
         CFM=CFM, DiT=DiT, BigVGAN=BigVGAN, BigVGANAttrDict=BigVGANAttrDict,
         Activation1d=Activation1d, SnakeBeta=SnakeBeta, Snake=Snake,
-        CFMv2=CFMv2, DiTv2=DiTv2, WN=WN, InterpolateRegulator=InterpolateRegulator,
+        CFMv2=CFMv2, DiTv2=DiTv2, WN=WN, InterpolateRegulator=InterpolateRegulator, mel_spectrogram=mel_spectrogram,
     )
     return ns

@@ -499,3 +499,48 @@ def interpolate_regulator(sd, x, ylens, n_blocks=4, f0=None, f0_condition=False,
     x = F.conv1d(x, sd[f"model.{k}.weight"], sd[f"model.{k}.bias"])                             # :55-57
     return x.transpose(1, 2).contiguous() * mask                                                # :131,140
 
+
+# ---------------------------------------------------------------------------------------------
+# Mel front-end - modules/audio.py:45-82
+# ---------------------------------------------------------------------------------------------
+def slaney_mel_filterbank(sr, n_fft, n_mels, fmin=0.0, fmax=None):
+    """librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax) with its defaults (htk=False, norm='slaney') -
+    the third-party function modules/audio.py:4,54 calls.  librosa is NOT installed in the authoring
+    container, so this restates librosa's published algorithm (Slaney's Auditory Toolbox mel scale:
+    linear below 1 kHz at 200/3 Hz per mel, log above with step ln(6.4)/27; triangular filters between
+    consecutive mel points; each filter scaled by 2 / bandwidth) and is unpinned by a librosa run."""
+    fmax = sr / 2.0 if fmax is None else float(fmax)
+
+    def hz2mel(f):
+        f = float(f)
+        return f / (200.0 / 3) if f < 1000.0 else 15.0 + math.log(f / 1000.0) / (math.log(6.4) / 27.0)
+
+    def mel2hz(m):
+        return (200.0 / 3) * m if m < 15.0 else 1000.0 * math.exp((math.log(6.4) / 27.0) * (m - 15.0))
+
+    lo, hi = hz2mel(fmin), hz2mel(fmax)
+    pts = [mel2hz(lo + (hi - lo) * i / (n_mels + 1)) for i in range(n_mels + 2)]
+    nb = 1 + n_fft // 2
+    fb = np.zeros((n_mels, nb), dtype=np.float64)
+    for i in range(n_mels):
+        left, centre, right = pts[i], pts[i + 1], pts[i + 2]
+        for k in range(nb):
+            f = (sr / 2.0) * k / (nb - 1)
+            up = (f - left) / (centre - left)
+            down = (right - f) / (right - centre)
+            fb[i, k] = max(0.0, min(up, down)) * 2.0 / (right - left)
+    return fb.astype(np.float32)
+
+
+def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin, fmax, center=False):
+    """modules/audio.py:45-82 line by line (torch CPU), with slaney_mel_filterbank for librosa_mel_fn."""
+    mel = torch.from_numpy(slaney_mel_filterbank(sampling_rate, n_fft, num_mels, fmin, fmax)).float()
+    window = torch.hann_window(win_size)
+    y = F.pad(y.unsqueeze(1), (int((n_fft - hop_size) / 2), int((n_fft - hop_size) / 2)), mode="reflect").squeeze(1)
+    spec = torch.view_as_real(torch.stft(y, n_fft, hop_length=hop_size, win_length=win_size, window=window,
+                                         center=center, pad_mode="reflect", normalized=False, onesided=True,
+                                         return_complex=True))
+    spec = torch.sqrt(spec.pow(2).sum(-1) + 1e-9)
+    spec = torch.matmul(mel, spec)
+    return torch.log(torch.clamp(spec, min=1e-5))
+

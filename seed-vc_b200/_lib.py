@@ -62,6 +62,9 @@ SIGNATURES = {
     "svc_groupnorm1_mish": [c_vp, c_ll, c_ll, c_vp, c_vp, c_float, c_vp, c_vp, c_ll, c_ll, c_int, c_int, c_int,
                             c_int, c_int, c_vp],
     "svc_mask_rows": [c_vp, c_ll, c_ll, c_vp, c_int, c_int, c_int, c_vp],
+    "svc_reflect_pad1d": [c_vp, c_ll, c_int, c_int, c_int, c_vp, c_ll, c_ll, c_vp],
+    "svc_stft_mag": [c_vp, c_ll, c_ll, c_int, c_float, c_vp, c_ll, c_vp],
+    "svc_log_clamp": [c_vp, c_ll, c_float, c_vp],
     "svc_crossfade_stitch": [c_vp, c_ll, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_ll, c_vp],
 }
 

@@ -519,6 +519,85 @@ extern "C" int svc_mask_rows(float* x, long long bstride, long long rstride, con
 }
 
 // ------------------------------------------------------------------------------------------
+// Mel front-end pieces (modules/audio.py:45-82).  The STFT itself is a segmented GEMM over
+// the padded audio viewed as rows of `hop` samples against the windowed DFT matrix.
+// ------------------------------------------------------------------------------------------
+// out[b, i] = y[b, reflect(i - pad)] for i < L + 2*pad, 0 for the tail up to out_len  (F.pad reflect, :58-61)
+__global__ void __launch_bounds__(256) reflect_pad1d_kernel(const float* __restrict__ y, long long ybs, int L,
+                                                            int pad, float* __restrict__ out, long long obs,
+                                                            long long out_len) {
+    const int b = blockIdx.y;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < out_len; i += gridDim.x * 256LL) {
+        float v = 0.f;
+        if (i < static_cast<long long>(L) + 2 * pad) {
+            long long j = i - pad;
+            if (j < 0) j = -j;
+            if (j >= L) j = 2LL * (L - 1) - j;
+            v = y[b * ybs + j];
+        }
+        out[b * obs + i] = v;
+    }
+}
+
+// mag[m, k] = sqrt(re[m,k]^2 + im[m,k]^2 + eps) with spec rows = [re_0..re_{nb-1} | im_0..im_{nb-1} | pad]  (:78)
+__global__ void __launch_bounds__(256) stft_mag_kernel(const float* __restrict__ spec, long long srs, int nb,
+                                                       float eps, float* __restrict__ mag, long long mrs,
+                                                       long long total) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+        const long long m = i / nb;
+        const int k = static_cast<int>(i - m * nb);
+        const float re = spec[m * srs + k], im = spec[m * srs + nb + k];
+        mag[m * mrs + k] = sqrtf(re * re + im * im + eps);
+    }
+}
+
+// x = log(max(x, clip))   (dynamic_range_compression_torch, :24-25)
+__global__ void __launch_bounds__(256) log_clamp_kernel(float* __restrict__ x, long long n, float clip) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL)
+        x[i] = logf(fmaxf(x[i], clip));
+}
+
+extern "C" int svc_reflect_pad1d(const float* y, long long y_bstride, int B, int L, int pad, float* out,
+                                 long long out_bstride, long long out_len, void* stream) {
+    if (B < 1 || L < 2 || pad < 0 || pad >= L || y == nullptr || out == nullptr ||
+        out_len < static_cast<long long>(L) + 2 * pad) {
+        svc_set_error("svc_reflect_pad1d: need 0 <= pad < L and out_len >= L + 2*pad");
+        return SVC_ERR_ARG;
+    }
+    const int blocks = static_cast<int>(std::min<long long>((out_len + 255) / 256, 1184));
+    reflect_pad1d_kernel<<<dim3(blocks, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        y, y_bstride, L, pad, out, out_bstride, out_len);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_stft_mag(const float* spec, long long spec_rstride, long long rows, int n_bins, float eps,
+                            float* mag, long long mag_rstride, void* stream) {
+    if (rows < 1 || n_bins < 1 || spec == nullptr || mag == nullptr) {
+        svc_set_error("svc_stft_mag: bad arguments");
+        return SVC_ERR_ARG;
+    }
+    const long long total = rows * n_bins;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 2368));
+    stft_mag_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(spec, spec_rstride, n_bins, eps, mag,
+                                                                          mag_rstride, total);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+extern "C" int svc_log_clamp(float* x, long long n, float clip, void* stream) {
+    if (n < 0 || (n > 0 && x == nullptr)) {
+        svc_set_error("svc_log_clamp: bad arguments");
+        return SVC_ERR_ARG;
+    }
+    if (n == 0) return SVC_OK;
+    const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 2368));
+    log_clamp_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, clip);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // Overlap / cos^2 crossfade stitching of vocoded chunks (inference.py:343-350,505-527;
 // seed_vc_wrapper.py:190-285): every chunk but the last drops its final `ov` samples, every chunk
 // but the first blends its first `ov` samples with the previous chunk's dropped tail.  The blend is

@@ -371,3 +371,30 @@ class Ops:
                                      self._stream()), "svc_mask_rows")
         self._t1()
 
+    # ------------------------------------------------------------------ mel front-end pieces
+    def reflect_pad1d(self, y, pad, out):
+        """out[b, :L+2*pad] = reflect-padded y[b]; zeros after (audio.py:58-61)."""
+        self._chk(y, out)
+        B, L = y.shape
+        assert y.dtype == torch.float32 and out.dtype == torch.float32 and y.stride(1) == 1 and out.stride(1) == 1
+        self._t0("misc")
+        check(self.lib.svc_reflect_pad1d(y.data_ptr(), y.stride(0), B, L, pad, out.data_ptr(), out.stride(0),
+                                         out.shape[1], self._stream()), "svc_reflect_pad1d")
+        self._t1()
+
+    def stft_mag(self, spec, n_bins, mag, eps=1e-9):
+        self._chk(spec, mag)
+        rows = spec.shape[0] * spec.shape[1]
+        assert spec.is_contiguous() and mag.is_contiguous() and mag.shape[-1] == n_bins
+        self._t0("misc")
+        check(self.lib.svc_stft_mag(spec.data_ptr(), spec.shape[-1], rows, n_bins, eps, mag.data_ptr(), n_bins,
+                                    self._stream()), "svc_stft_mag")
+        self._t1()
+
+    def log_clamp(self, x, clip=1e-5):
+        self._chk(x)
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        self._t0("misc")
+        check(self.lib.svc_log_clamp(x.data_ptr(), x.numel(), clip, self._stream()), "svc_log_clamp")
+        self._t1()
+

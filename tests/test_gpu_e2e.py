@@ -259,3 +259,24 @@ def test_cuda_graph_replay_equals_eager():
         mel = cfm.solve_euler(z.clone(), lens, prompt, mu, style, None, t_span, cfg)
         want = voc(mel[:, :, Tp:].contiguous())
         assert torch.equal(got, want)
+
+
+def test_mel_frontend_golden():
+    """mel_spectrogram as reflect pad + segmented-GEMM STFT + mel GEMM vs the REAL reference
+    function's outputs (torch.stft path); fp32 arithmetic, tolerance 1e-3 like the fp32 mode of the path."""
+    import json
+    import os
+
+    import numpy as np
+    import gen_golden_mel as gm
+    from seedvc_b200.audio import mel_spectrogram
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "mel_kat.npz"))
+    for name, m in json.loads(str(z["meta"])).items():
+        y = gm.audio(name, m["B"], m["L"]).to(DEV)
+        got = mel_spectrogram(y, **m["kw"])
+        e = rel_l2(got.cpu(), z[name])
+        print(f"mel front-end {name} rel-L2 {e:.2e} max|d| {float((got.cpu() - torch.from_numpy(z[name])).abs().max()):.2e}")
+        assert tuple(got.shape) == z[name].shape and e < 1e-3
+    with pytest.raises(RuntimeError):
+        mel_spectrogram(torch.zeros(1, 4096), 1024, 80, 22050, 256, 1024, 0, None)

@@ -119,3 +119,30 @@ def test_length_regulator_oracle_against_reference_golden():
         assert y.shape == want.shape
         e = float((y - want).norm() / want.norm())
         assert e < 1e-5, (name, e)
+
+
+def test_mel_frontend_oracle_against_reference_golden():
+    """oracle.mel_spectrogram vs the REAL reference function (oracle/gen_golden_mel.py); and the package's
+    Slaney filterbank vs the oracle's independent restatement (librosa itself is not available)."""
+    import json
+    import os
+
+    import numpy as np
+    import torch
+    import gen_golden_mel as gm
+    import seedvc_oracle as orc
+    from seedvc_b200.audio import mel_filterbank
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "mel_kat.npz"))
+    for name, m in json.loads(str(z["meta"])).items():
+        y = gm.audio(name, m["B"], m["L"])
+        got = orc.mel_spectrogram(y, **m["kw"])
+        want = torch.from_numpy(z[name])
+        assert got.shape == want.shape
+        assert float((got - want).norm() / want.norm()) < 1e-6, name
+    for sr, n_fft, n_mels, fmax in [(22050, 1024, 80, None), (44100, 2048, 128, None), (22050, 1024, 80, 8000)]:
+        a = mel_filterbank(sr, n_fft, n_mels, 0, fmax)
+        b = orc.slaney_mel_filterbank(sr, n_fft, n_mels, 0, fmax)
+        assert a.shape == b.shape == (n_mels, n_fft // 2 + 1)
+        assert np.abs(a - b).max() < 1e-7 * max(1.0, np.abs(b).max())
+        assert (a.sum(1) > 0).all()
