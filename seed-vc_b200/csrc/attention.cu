@@ -33,7 +33,7 @@ constexpr int AT_QT = 3;     // Q tiles per CTA = softmax groups taking turns on
 constexpr int AT_BN = 64;    // keys per block
 constexpr int AT_HD = 64;
 #ifndef AT_KST_V
-#define AT_KST_V 6
+#define AT_KST_V 4
 #endif
 #ifndef AT_POLY_EVERY
 #define AT_POLY_EVERY 3   // every 3rd key pair takes the FMA-pipe exp2 (0 = all on MUFU)
