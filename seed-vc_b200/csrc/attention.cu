@@ -3,12 +3,10 @@
 // (reference: modules/diffusion_transformer.py:255,518-520).  q and k arrive already rotated
 // (RoPE) and q pre-scaled by 1/sqrt(64) from the wqkv GEMM epilogue.
 //
-// bf16: flash-style tcgen05 kernel.  One CTA = 128 queries of one (batch, head).
-//   warp 0  : TMA producer (Q once, then K_j / V_j tiles of 128 keys through mbarrier rings)
-//   warp 1  : MMA issuer.  S_j = Q K_j^T -> TMEM (2 buffers of 128 fp32 columns),
-//             O_j = P_j V_j -> TMEM (2 buffers of 64 columns, V consumed MN-major)
-//   warps 2-5: one query row per thread: online softmax on S_j (tcgen05.ld), P_j -> bf16 ->
-//             128B-swizzled smem for the PV MMA, running O in registers rescaled per block.
+// bf16: flash-style tcgen05 kernel, one CTA = 384 queries (three Q tiles) of one (batch, head), keys in
+//   blocks of 64: TMA producer warp, one MMA-issuing warp per Q tile, three softmax warpgroups (one
+//   query row per thread), S / O / P all in TMEM (P is the A operand of the PV MMA straight from TMEM).
+//   Details and the measured bounds are in the comment above attention_tc_kernel.
 // fp32: FFMA kernel, one query per thread ("fp32 mode").
 #include <stdlib.h>
 

@@ -1,10 +1,14 @@
 // svc_gemm: every dense contraction of the hot path (Linear / concat-free Linear / Conv1d taps /
 // polyphase ConvTranspose1d) as one segmented GEMM with a fused epilogue.
 //
-//  * bf16 operands  -> tcgen05.mma (UMMA 128 x N x 16, fp32 accumulators in TMEM), operands
-//                      staged by TMA (cp.async.bulk.tensor, 128B swizzle) through an mbarrier
-//                      ring; warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-//                      warps 2-5 = epilogue (tcgen05.ld -> registers -> fused epilogue -> HBM).
+//  * bf16 operands  -> persistent tcgen05 kernel (grid <= 148, n-fastest tile order): UMMA 128 x N x 16
+//                      with fp32 accumulators in TMEM (two buffers, so the epilogue of tile i overlaps
+//                      the MMAs of tile i+1); operands staged by TMA (cp.async.bulk.tensor, 128B
+//                      swizzle) through a 4-8 stage mbarrier ring that runs ahead across tiles;
+//                      warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = two
+//                      epilogue groups.  Epilogues (template EPI): register / LSU (any pattern),
+//                      direct row-layout TMA store (bf16 or fp32 tile, fp32 reduce-add for in-place
+//                      residuals), two-output variant; see gemm_tc_kernel.
 //  * fp32 operands  -> FFMA shared-memory tiled mainloop ("fp32 mode", small-M conditioning
 //                      GEMMs, and a debug cross-check of the tensor-core path).
 //
