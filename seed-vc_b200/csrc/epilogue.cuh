@@ -15,6 +15,7 @@ struct EpiParams {
     const float* rope_tab_t;   // pair-major (32, rope_ld, 2) copy, or nullptr
     int rope_ld;
     int rope_cols, rope_pos0, q_cols;
+    int rope_mod;              // > 0: rows are (batch, frame) flattened, position = rope_pos0 + row % rope_mod
     float q_scale;
     const float* gate;
     long long gate_bstride;
@@ -44,6 +45,7 @@ inline EpiParams make_epi_params(const svc_gemm_desc& d) {
     e.rope_ld = d.rope_ld;
     e.rope_cols = d.rope_cols;
     e.rope_pos0 = d.rope_pos0;
+    e.rope_mod = 0;
     e.q_cols = d.q_cols;
     e.q_scale = d.q_scale;
     e.gate = d.gate;

@@ -444,7 +444,8 @@ __device__ __forceinline__ void epilogue_item_tma(const TcParams& p, float* stag
 // consecutive lanes = consecutive positions = consecutive addresses
 __device__ __forceinline__ void rope_prefetch_rows(const EpiParams& e, int c0, int lane, int t_base,
                                                    float4 (&rr)[8]) {
-    const int pos = min(e.rope_pos0 + t_base + lane, e.rope_ld - 1);
+    const int row = t_base + lane;
+    const int pos = min(e.rope_pos0 + (e.rope_mod > 0 ? row % e.rope_mod : row), e.rope_ld - 1);
     const float2* tab = reinterpret_cast<const float2*>(e.rope_tab_t) +
                         static_cast<long long>((c0 & 63) >> 1) * e.rope_ld + pos;
 #pragma unroll
@@ -979,7 +980,41 @@ static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
                     : launch_tc_epi<BN, STAGES, 1>(p, m_tiles, stream);
 }
 
-static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
+// Rows of different batch entries can share M tiles when every operand / output is contiguous across the
+// batch and nothing in the epilogue is per batch entry: (B, T) -> (1, B*T).  T = 2581 wastes 4 % of every
+// 128-row tile grid per batch entry (21 tiles for 20.16); flattened, config 2 runs 1291 tiles instead of 1344.
+static bool flatten_batch(svc_gemm_desc& d, int* rope_mod) {
+    *rope_mod = 0;
+    static const int off = getenv("SVC_NO_FLATTEN") ? 1 : 0;
+    if (off || d.B <= 1 || d.rowbias != nullptr || d.gate != nullptr) return false;
+    const long long T = d.T;
+    for (int s = 0; s < d.n_seg; ++s)
+        if (d.a_shift[s] != 0 || d.a_rows[s] != d.T || d.a_bstride[s] != T * d.a_rstride[s]) return false;
+    if (d.out_f32 != nullptr && d.of_bstride != T * d.of_rstride) return false;
+    if (d.out_op != nullptr && d.oo_bstride != T * d.oo_rstride) return false;
+    if (d.res != nullptr && d.res_bstride != T * d.res_rstride) return false;
+    if (d.act == SVC_ACT_ROPE) {
+        // positions restart per batch entry: only the row-layout epilogue knows how (rope_mod); make sure
+        // that epilogue will be the one selected
+        const bool direct_rope = d.rope_tab_t != nullptr && d.rope_ld > 0 && d.N % 4 == 0 &&
+                                 reinterpret_cast<uintptr_t>(d.rope_tab_t) % 8 == 0 && d.out_op != nullptr &&
+                                 d.out_f32 == nullptr && d.res == nullptr && !d.accumulate &&
+                                 reinterpret_cast<uintptr_t>(d.out_op) % 16 == 0 && (d.oo_rstride * 2) % 16 == 0 &&
+                                 !getenv("SVC_NO_DIRECT") && !getenv("SVC_NO_TMA_STORE");
+        if (!direct_rope) return false;
+        *rope_mod = d.T;
+    }
+    if (T * d.B > 0x7fffffffLL) return false;
+    d.T = static_cast<int>(T * d.B);
+    d.B = 1;
+    for (int s = 0; s < d.n_seg; ++s) d.a_rows[s] = d.T;
+    return true;
+}
+
+static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
+    svc_gemm_desc d = d_in;
+    int rope_mod = 0;
+    const bool flattened = flatten_batch(d, &rope_mod);
     TcParams p;
     memset(&p, 0, sizeof(p));
     int BN = 128;
@@ -1048,6 +1083,7 @@ static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
     p.tiles_per_batch = (d.T + BM - 1) / BM;
     p.n_tiles = (d.N + BN - 1) / BN;
     p.epi = make_epi_params(d);
+    p.epi.rope_mod = rope_mod;
     // ---- TMA-store epilogue when the output pattern allows it ------------------------------
     static const int no_tma_store = getenv("SVC_NO_TMA_STORE") ? 1 : 0;
     static const int no_direct = getenv("SVC_NO_DIRECT") ? 1 : 0;
@@ -1086,6 +1122,10 @@ static int gemm_tc(const svc_gemm_desc& d, cudaStream_t stream) {
         }
     }
     if (BN < 64 && pair_act) p.store_mode = 0;
+    if (flattened && rope_mod > 0 && !(p.direct && p.store_mode == 1)) {
+        svc_set_error("svc_gemm: internal - flattened RoPE GEMM did not get the row-layout epilogue");
+        return SVC_ERR_ARG;
+    }
     const int m_tiles = d.B * p.tiles_per_batch;
     switch (BN) {
         case 32: return launch_tc<32, 8>(p, m_tiles, stream);
