@@ -580,6 +580,7 @@ template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
     using S = TcSmem<BN, STAGES, EPI == 5 ? 6144 : 4096>;
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    constexpr int kTmemCols = 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;   // power of two
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -610,7 +611,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         mbar_fence_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 2 * ACC_COLS);
+        tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -808,7 +809,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * ACC_COLS);
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -1021,6 +1022,7 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
     if (d.N <= 32) BN = 32;
     else if (d.N <= 64) BN = 64;
     else if (d.N <= 128) BN = 128;
+    else if ((d.N == 192 || d.N == 384) && !getenv("SVC_NO_BN192")) BN = 192;   // exact tiles: no half-empty second tile / W box
     else BN = 256;
     // ---- A maps: one per distinct view ---------------------------------------------------
     struct AKey { const void* ptr; long long bs, rs; int rows, K; };
@@ -1131,6 +1133,7 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
         case 32: return launch_tc<32, 8>(p, m_tiles, stream);
         case 64: return launch_tc<64, 8>(p, m_tiles, stream);
         case 128: return launch_tc<128, 6>(p, m_tiles, stream);
+        case 192: return launch_tc<192, 4>(p, m_tiles, stream);
         default: return launch_tc<256, 4>(p, m_tiles, stream);
     }
 }
