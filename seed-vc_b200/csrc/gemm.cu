@@ -1021,6 +1021,7 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
     int BN = 128;
     if (d.N <= 32) BN = 32;
     else if (d.N <= 64) BN = 64;
+    else if (d.N == 96 && !getenv("SVC_NO_BN96")) BN = 96;      // W box of exactly one tap's rows
     else if (d.N <= 128) BN = 128;
     else if ((d.N == 192 || d.N == 384) && !getenv("SVC_NO_BN192")) BN = 192;   // exact tiles: no half-empty second tile / W box
     else BN = 256;
@@ -1132,6 +1133,7 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
     switch (BN) {
         case 32: return launch_tc<32, 8>(p, m_tiles, stream);
         case 64: return launch_tc<64, 8>(p, m_tiles, stream);
+        case 96: return launch_tc<96, 6>(p, m_tiles, stream);
         case 128: return launch_tc<128, 6>(p, m_tiles, stream);
         case 192: return launch_tc<192, 4>(p, m_tiles, stream);
         default: return launch_tc<256, 4>(p, m_tiles, stream);
