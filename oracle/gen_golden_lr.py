@@ -30,6 +30,22 @@ CASES = [
 ]
 
 
+# v2 (modules/v2/length_regulator.py): (name, kwargs, B, Tin, ylens)
+CASES_V2 = [
+    ("v2_cfm", dict(channels=512, is_discrete=True, codebook_size=2048, sampling_ratios=[1, 1, 1, 1],
+                    f0_condition=False), 2, 40, [69, 52]),
+    ("v2_out256", dict(channels=512, is_discrete=True, codebook_size=2048, sampling_ratios=[1, 1], out_channels=256,
+                       f0_condition=False), 1, 33, [57]),
+    ("v2_ar", dict(channels=768, is_discrete=True, codebook_size=32, sampling_ratios=[], f0_condition=False),
+     2, 29, [29, 29]),
+]
+
+
+def tokens(name, B, Tin, codebook):
+    g = torch.Generator().manual_seed(71 + [c[0] for c in CASES_V2].index(name))
+    return torch.randint(0, codebook, (B, Tin), generator=g)
+
+
 def inputs(name, B, Tin, Cin, Tf0=None):
     g = torch.Generator().manual_seed(31 + [c[0] for c in CASES].index(name))
     x = torch.randn(B, Tin, Cin, generator=g)
@@ -52,6 +68,17 @@ def main():
             y, olens, *_ = m(x, ylens=torch.tensor(ylens), n_quantizers=3, f0=f0)
         out[name] = y.numpy()
         meta[name] = dict(kw=kw, B=B, Tin=Tin, ylens=ylens, f0=f0mode,
+                          keys={k: list(v.shape) for k, v in m.state_dict().items()})
+        print(name, tuple(y.shape), "mean|y| =", float(y.abs().mean()))
+    for name, kw, B, Tin, ylens in CASES_V2:
+        m = ns.InterpolateRegulatorV2(**kw).eval()
+        with torch.no_grad():
+            synth.fill_parameters_(m, seed=0, prefix="cfm_length_regulator.")
+        tok = tokens(name, B, Tin, kw["codebook_size"])
+        with torch.no_grad():
+            y, olens = m(tok, ylens=torch.tensor(ylens), f0=None)
+        out[name] = y.numpy()
+        meta[name] = dict(kw=kw, B=B, Tin=Tin, ylens=ylens, v2=True,
                           keys={k: list(v.shape) for k, v in m.state_dict().items()})
         print(name, tuple(y.shape), "mean|y| =", float(y.abs().mean()))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "length_regulator.npz"), meta=json.dumps(meta), **out)

@@ -97,10 +97,11 @@ def load():
     from modules.wavenet import WN  # noqa: E402
     from modules.length_regulator import InterpolateRegulator  # noqa: E402
     from modules.audio import mel_spectrogram  # noqa: E402
+    from modules.v2.length_regulator import InterpolateRegulator as InterpolateRegulatorV2  # noqa: E402
 
     ns = types.SimpleNamespace(
         CFM=CFM, DiT=DiT, BigVGAN=BigVGAN, BigVGANAttrDict=BigVGANAttrDict,
         Activation1d=Activation1d, SnakeBeta=SnakeBeta, Snake=Snake,
-        CFMv2=CFMv2, DiTv2=DiTv2, WN=WN, InterpolateRegulator=InterpolateRegulator, mel_spectrogram=mel_spectrogram,
+        CFMv2=CFMv2, DiTv2=DiTv2, WN=WN, InterpolateRegulator=InterpolateRegulator, mel_spectrogram=mel_spectrogram, InterpolateRegulatorV2=InterpolateRegulatorV2,
     )
     return ns

@@ -544,3 +544,24 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
     spec = torch.matmul(mel, spec)
     return torch.log(torch.clamp(spec, min=1e-5))
 
+
+def interpolate_regulator_v2(sd, tokens, ylens, n_blocks=4):
+    """modules/v2/length_regulator.py:74-110, discrete branch without F0: embedding -> nearest
+    interpolation (or none when ``n_blocks == 0``, the ar_length_regulator) -> conv stack -> [1x1 conv]."""
+    x = F.embedding(tokens if tokens.dim() == 2 else tokens[:, 0], sd["embedding.weight"])      # :76-79
+    if n_blocks > 0:
+        Tout = int(ylens.max())
+        mask = (torch.arange(Tout)[None, :] < ylens[:, None]).unsqueeze(-1)                     # :85
+        x = F.interpolate(x.transpose(1, 2).contiguous(), size=Tout, mode="nearest")           # :86
+    else:
+        x, mask = x.transpose(1, 2).contiguous(), None                                          # :88-89
+    for i in range(n_blocks):
+        x = F.conv1d(x, sd[f"model.{3 * i}.weight"], sd[f"model.{3 * i}.bias"], padding=1)
+        x = F.group_norm(x, 1, sd[f"model.{3 * i + 1}.weight"], sd[f"model.{3 * i + 1}.bias"], 1e-5)
+        x = F.mish(x)
+    k = 3 * n_blocks
+    if f"model.{k}.weight" in sd:                                                               # :53-55
+        x = F.conv1d(x, sd[f"model.{k}.weight"], sd[f"model.{k}.bias"])
+    out = x.transpose(1, 2).contiguous()
+    return out * mask if mask is not None else out                                              # :107-108
+

@@ -53,10 +53,10 @@ def nearest_index(n_in: int, n_out: int) -> np.ndarray:
 class InterpolateRegulator(nn.Module):
     def __init__(self, channels, sampling_ratios, is_discrete=False, in_channels=None, vector_quantize=False,
                  codebook_size=1024, out_channels=None, groups=1, n_codebooks=1, quantizer_dropout=0.0,
-                 f0_condition=False, n_f0_bins=512, mode: str = "bf16"):
+                 f0_condition=False, n_f0_bins=512, mode: str = "bf16", v2: bool = False):
         super().__init__()
-        if is_discrete or vector_quantize or n_codebooks != 1:
-            raise NotImplementedError("only the continuous, non-VQ InterpolateRegulator of the v1 presets")
+        if vector_quantize or n_codebooks != 1:
+            raise NotImplementedError("vector-quantised / multi-codebook InterpolateRegulator is not built")
         if groups != 1:
             raise NotImplementedError("GroupNorm with one group only (the reference default)")
         self.sampling_ratios = sampling_ratios
@@ -65,8 +65,10 @@ class InterpolateRegulator(nn.Module):
         self.interpolate = len(sampling_ratios) > 0
         for _ in sampling_ratios:                     # parameter containers with the reference's names
             model.extend([nn.Conv1d(channels, channels, 3, 1, 1), nn.GroupNorm(groups, channels), nn.Mish()])
-        model.append(nn.Conv1d(channels, out_channels, 1, 1))
+        # v2 (modules/v2/length_regulator.py:53-55) drops the 1x1 conv when the widths agree
+        model.append(nn.Identity() if (v2 and channels == out_channels) else nn.Conv1d(channels, out_channels, 1, 1))
         self.model = nn.Sequential(*model)
+        self.v2 = v2
         self.embedding = nn.Embedding(codebook_size, channels)
         self.is_discrete = is_discrete
         self.mask_token = nn.Parameter(torch.zeros(1, channels))
@@ -77,7 +79,8 @@ class InterpolateRegulator(nn.Module):
             self.f0_embedding = nn.Embedding(n_f0_bins, channels)
             self.n_f0_bins = n_f0_bins
             self.f0_mask = nn.Parameter(torch.zeros(1, channels))
-        self.content_in_proj = nn.Linear(in_channels, channels)
+        if not is_discrete:
+            self.content_in_proj = nn.Linear(in_channels, channels)
         self.channels, self.out_channels = channels, out_channels
         self.mode = mode
         self._prep = None
@@ -86,23 +89,28 @@ class InterpolateRegulator(nn.Module):
         self.mode, self._prep = mode, None
 
     def _prepare(self):
-        dev = self.content_in_proj.weight.device
+        dev = self.mask_token.device
         key = (self.mode, str(dev))
         if self._prep is not None and self._prep["key"] == key:
             return self._prep
         ops = Ops(self.mode)
         od = ops.op_dtype
         f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
-        w = {"key": key, "ops": ops,
-             "proj_w": f(self.content_in_proj.weight).to(od), "proj_b": f(self.content_in_proj.bias), "blocks": []}
+        w = {"key": key, "ops": ops, "blocks": []}
+        if self.is_discrete:
+            w["emb"] = f(self.embedding.weight)
+            w["zero_row"] = torch.zeros(1, 1, self.channels, dtype=torch.float32, device=dev)
+        else:
+            w["proj_w"], w["proj_b"] = f(self.content_in_proj.weight).to(od), f(self.content_in_proj.bias)
         mods = list(self.model)
         for i in range(0, len(mods) - 1, 3):
             conv, gn = mods[i], mods[i + 1]
             w["blocks"].append(dict(w=f(conv.weight).permute(2, 0, 1).contiguous().to(od), b=f(conv.bias),
                                     g=f(gn.weight), beta=f(gn.bias), eps=gn.eps))
         last = mods[-1]
-        w["out_w"] = f(last.weight)[:, :, 0].contiguous().to(od)
-        w["out_b"] = f(last.bias)
+        if isinstance(last, nn.Conv1d):
+            w["out_w"] = f(last.weight)[:, :, 0].contiguous().to(od)
+            w["out_b"] = f(last.bias)
         if self.f0_condition:
             w["f0_emb"] = f(self.f0_embedding.weight)
             w["f0_mask"] = f(self.f0_mask).view(-1)
@@ -120,14 +128,18 @@ class InterpolateRegulator(nn.Module):
         w = self._prepare()
         ops, od = w["ops"], w["ops"].op_dtype
         dev = x.device
-        B, Tin, Cin = x.shape
         D = self.channels
-        xin = x.to(torch.float32).contiguous()
-        x_op = xin if od == torch.float32 else ops.empty(B, Tin, Cin, device=dev)
-        if od != torch.float32:
-            ops.cast(xin, x_op)
-        h0 = torch.empty(B, Tin, D, dtype=torch.float32, device=dev)
-        ops.gemm([(x_op, 0, w["proj_w"])], D, B=B, T=Tin, bias=w["proj_b"], out_f32=h0)
+        if self.is_discrete:                         # token ids: (B, T) or (B, n_codebooks, T) -> first book
+            tok = (x if x.dim() == 2 else x[:, 0]).to(torch.int32).contiguous()
+            B, Tin = tok.shape
+        else:
+            B, Tin, Cin = x.shape
+            xin = x.to(torch.float32).contiguous()
+            x_op = xin if od == torch.float32 else ops.empty(B, Tin, Cin, device=dev)
+            if od != torch.float32:
+                ops.cast(xin, x_op)
+            h0 = torch.empty(B, Tin, D, dtype=torch.float32, device=dev)
+            ops.gemm([(x_op, 0, w["proj_w"])], D, B=B, T=Tin, bias=w["proj_b"], out_f32=h0)
         if self.interpolate:
             Tout = int(ylens.max())
             idx = torch.from_numpy(nearest_index(Tin, Tout)).to(dev)
@@ -135,22 +147,41 @@ class InterpolateRegulator(nn.Module):
         else:                                        # length_regulator.py:116-119
             Tout = Tin
             idx = torch.arange(Tin, dtype=torch.int32, device=dev)
-            olens = ylens.clamp(max=Tin).long()
-        cur = ops.empty(B, Tout, D, device=dev)
-        kw = {}
-        if self.f0_condition:
-            if f0 is None:
-                kw["add_vec"] = w["f0_mask"]
-            else:
-                q = f0_to_coarse(f0.to(dev), self.n_f0_bins).clamp(0, self.n_f0_bins - 1).to(torch.int32).contiguous()
-                kw.update(emb=w["f0_emb"], emb_q=q,
-                          emb_idx=torch.from_numpy(nearest_index(q.shape[1], Tout)).to(dev))
-        ops.interp_rows(h0, idx, cur, **kw)
+            olens = ylens if self.v2 else ylens.clamp(max=Tin).long()
+        bare = not w["blocks"] and "out_w" not in w       # no conv stack at all (v2 ar_length_regulator)
+        cur = torch.empty(B, Tout, D, dtype=torch.float32, device=dev) if bare else ops.empty(B, Tout, D, device=dev)
+        if self.is_discrete:
+            if self.f0_condition:
+                raise NotImplementedError("discrete tokens together with F0 conditioning (no preset uses it)")
+            # embedding lookup + nearest interpolation in one gather: zero source row + embedding add
+            ops.interp_rows(w["zero_row"].expand(B, 1, D), torch.zeros(Tout, dtype=torch.int32, device=dev), cur,
+                            emb=w["emb"], emb_q=tok, emb_idx=idx)
+        else:
+            kw = {}
+            if self.f0_condition:
+                if f0 is None:
+                    kw["add_vec"] = w["f0_mask"]
+                else:
+                    q = f0_to_coarse(f0.to(dev), self.n_f0_bins).clamp(0, self.n_f0_bins - 1).to(torch.int32).contiguous()
+                    kw.update(emb=w["f0_emb"], emb_q=q,
+                              emb_idx=torch.from_numpy(nearest_index(q.shape[1], Tout)).to(dev))
+            ops.interp_rows(h0, idx, cur, **kw)
         y = torch.empty(B, Tout, D, dtype=torch.float32, device=dev)
+        y_pre, last_blk = None, None
         for blk in w["blocks"]:
             ops.gemm([(cur, s - 1, blk["w"][s]) for s in range(3)], D, B=B, T=Tout, bias=blk["b"], out_f32=y)
             ops.groupnorm1_mish(y, blk["g"], blk["beta"], cur, eps=blk["eps"])
-        out = torch.empty(B, Tout, self.out_channels, dtype=torch.float32, device=dev)
-        ops.gemm([(cur, 0, w["out_w"])], self.out_channels, B=B, T=Tout, bias=w["out_b"], out_f32=out)
-        ops.mask_rows(out, olens.to(device=dev, dtype=torch.int32).contiguous())
+            y_pre, last_blk = y, blk
+        if "out_w" in w:
+            out = torch.empty(B, Tout, self.out_channels, dtype=torch.float32, device=dev)
+            ops.gemm([(cur, 0, w["out_w"])], self.out_channels, B=B, T=Tout, bias=w["out_b"], out_f32=out)
+        elif bare:
+            out = cur
+        else:                                        # Identity tail: last block's activation, in fp32
+            out = y
+            ops.groupnorm1_mish(y_pre, last_blk["g"], last_blk["beta"], out, eps=last_blk["eps"])
+        if self.interpolate or not self.v2:          # v2 without interpolation applies no mask (:90-93,:108)
+            ops.mask_rows(out, olens.to(device=dev, dtype=torch.int32).contiguous())
+        if self.v2:
+            return out, olens                        # modules/v2/length_regulator.py:110
         return out, olens, None, None, None

@@ -109,12 +109,17 @@ def test_length_regulator_oracle_against_reference_golden():
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "length_regulator.npz"))
     meta = json.loads(str(z["meta"]))
     for name, m in meta.items():
-        sd = synth.synth_state_dict({"length_regulator." + k: v for k, v in m["keys"].items()})
-        sd = {k[len("length_regulator."):]: v for k, v in sd.items()}
-        x, f0 = gl.inputs(name, m["B"], m["Tin"], m["kw"]["in_channels"], Tf0=m["Tin"] + 3 if m["f0"] else None)
-        y = orc.interpolate_regulator(sd, x, torch.tensor(m["ylens"]), f0=f0,
-                                      f0_condition=m["kw"].get("f0_condition", False),
-                                      n_f0_bins=m["kw"].get("n_f0_bins", 512))
+        pre = "cfm_length_regulator." if m.get("v2") else "length_regulator."
+        sd = synth.synth_state_dict({pre + k: v for k, v in m["keys"].items()})
+        sd = {k[len(pre):]: v for k, v in sd.items()}
+        if m.get("v2"):
+            tok = gl.tokens(name, m["B"], m["Tin"], m["kw"]["codebook_size"])
+            y = orc.interpolate_regulator_v2(sd, tok, torch.tensor(m["ylens"]), n_blocks=len(m["kw"]["sampling_ratios"]))
+        else:
+            x, f0 = gl.inputs(name, m["B"], m["Tin"], m["kw"]["in_channels"], Tf0=m["Tin"] + 3 if m["f0"] else None)
+            y = orc.interpolate_regulator(sd, x, torch.tensor(m["ylens"]), f0=f0,
+                                          f0_condition=m["kw"].get("f0_condition", False),
+                                          n_f0_bins=m["kw"].get("n_f0_bins", 512))
         want = torch.from_numpy(z[name])
         assert y.shape == want.shape
         e = float((y - want).norm() / want.norm())
