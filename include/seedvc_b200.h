@@ -222,6 +222,16 @@ int svc_crossfade_stitch(const float* waves, long long wave_stride, const int* l
                          int n_chunks, int overlap, const double* fade_in, const double* fade_out,
                          float* out, long long total, void* stream);
 
+/* Streaming SOLA stitch, one launch for B concurrent streams (real-time-gui.py:1103-1137): offset[b] =
+ * argmax_o  sum_i x[o+i]*buf[i] / sqrt(sum_i x[o+i]^2 + 1e-8), o in [0, search]; out[b, i] = x[off+i] for
+ * i in [sb, block), x[off+i]*fade_in[i] + buf[i]*fade_out[i] for i < sb; then buf[b, :] = the next sb
+ * samples after the block (the state carried to the next tick).  infer (B, infer_len) fp32,
+ * sola_buf (B, sb) fp32 in/out, fade_in / fade_out (sb) fp32, out (B, block) fp32, offsets (B) int32. */
+int svc_sola_stitch(const float* infer, long long infer_bstride, int infer_len, float* sola_buf,
+                    long long buf_bstride, const float* fade_in, const float* fade_out, float* out,
+                    long long out_bstride, int* offsets, int B, int sola_buffer_frame, int sola_search_frame,
+                    int block_frame, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

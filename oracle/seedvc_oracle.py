@@ -565,3 +565,19 @@ def interpolate_regulator_v2(sd, tokens, ylens, n_blocks=4):
     out = x.transpose(1, 2).contiguous()
     return out * mask if mask is not None else out                                              # :107-108
 
+
+def sola_step(infer_wav, sola_buffer, fade_in_window, fade_out_window, sola_buffer_frame, sola_search_frame,
+              block_frame):
+    """One stream, one tick of real-time-gui.py:1103-1137.  Returns (out block, new sola_buffer, offset)."""
+    infer_wav = infer_wav.clone()
+    conv_input = infer_wav[None, None, :sola_buffer_frame + sola_search_frame]                # :1104-1106
+    cor_nom = F.conv1d(conv_input, sola_buffer[None, None, :])                                # :1108
+    cor_den = torch.sqrt(F.conv1d(conv_input ** 2, torch.ones(1, 1, sola_buffer_frame)) + 1e-8)   # :1109-1115
+    tensor = cor_nom[0, 0] / cor_den[0, 0]
+    sola_offset = int(torch.argmax(tensor, dim=0).item()) if tensor.numel() > 1 else int(tensor.item())
+    infer_wav = infer_wav[sola_offset:]                                                       # :1130
+    infer_wav[:sola_buffer_frame] *= fade_in_window                                           # :1131
+    infer_wav[:sola_buffer_frame] += sola_buffer * fade_out_window                            # :1132-1134
+    new_buffer = infer_wav[block_frame:block_frame + sola_buffer_frame].clone()               # :1135-1137
+    return infer_wav[:block_frame].clone(), new_buffer, sola_offset
+

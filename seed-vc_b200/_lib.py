@@ -65,6 +65,8 @@ SIGNATURES = {
     "svc_reflect_pad1d": [c_vp, c_ll, c_int, c_int, c_int, c_vp, c_ll, c_ll, c_vp],
     "svc_stft_mag": [c_vp, c_ll, c_ll, c_int, c_float, c_vp, c_ll, c_vp],
     "svc_log_clamp": [c_vp, c_ll, c_float, c_vp],
+    "svc_sola_stitch": [c_vp, c_ll, c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_ll, c_vp, c_int, c_int, c_int, c_int,
+                        c_vp],
     "svc_crossfade_stitch": [c_vp, c_ll, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_ll, c_vp],
 }
 

@@ -641,6 +641,94 @@ extern "C" int svc_crossfade_stitch(const float* waves, long long wave_stride, c
 }
 
 // ------------------------------------------------------------------------------------------
+// Streaming SOLA stitch (real-time-gui.py:1103-1137): per stream, find the offset in [0, search] that
+// maximises the normalised cross-correlation between the new block's head and the kept tail of the
+// previous block, cut there, crossfade the first `sb` samples with the kept tail, keep the next tail.
+// One CTA per stream; the window and the tail sit in shared memory.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sola_stitch_kernel(const float* __restrict__ infer, long long ibs,
+                                                          float* __restrict__ sola_buf, long long bbs,
+                                                          const float* __restrict__ fade_in,
+                                                          const float* __restrict__ fade_out,
+                                                          float* __restrict__ out, long long obs,
+                                                          int* __restrict__ offsets, int sb, int search,
+                                                          int block) {
+    extern __shared__ float sm[];
+    float* xs = sm;                    // sb + search samples of the new block's head
+    float* bs = xs + sb + search;      // sb samples kept from the previous block
+    __shared__ float best_v[256];
+    __shared__ int best_o[256];
+    const int b = blockIdx.x;
+    const float* x = infer + b * ibs;
+    float* buf = sola_buf + b * bbs;
+    for (int i = threadIdx.x; i < sb + search; i += 256) xs[i] = x[i];
+    for (int i = threadIdx.x; i < sb; i += 256) bs[i] = buf[i];
+    __syncthreads();
+    float bv = -INFINITY;
+    int bo = 0x7fffffff;
+    for (int o = threadIdx.x; o <= search; o += 256) {
+        float nom = 0.f, den = 0.f;
+        for (int i = 0; i < sb; ++i) {
+            const float v = xs[o + i];
+            nom = fmaf(v, bs[i], nom);
+            den = fmaf(v, v, den);
+        }
+        const float c = nom / sqrtf(den + 1e-8f);
+        if (c > bv) bv = c, bo = o;                   // first maximum within this thread's offsets
+    }
+    best_v[threadIdx.x] = bv;
+    best_o[threadIdx.x] = bo;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {               // argmax, ties -> smallest offset (torch.argmax)
+        if (threadIdx.x < s) {
+            const float v2 = best_v[threadIdx.x + s];
+            const int o2 = best_o[threadIdx.x + s];
+            if (v2 > best_v[threadIdx.x] || (v2 == best_v[threadIdx.x] && o2 < best_o[threadIdx.x]))
+                best_v[threadIdx.x] = v2, best_o[threadIdx.x] = o2;
+        }
+        __syncthreads();
+    }
+    const int off = best_o[0];
+    if (threadIdx.x == 0) offsets[b] = off;
+    // faded(i) = x[off+i]*fade_in[i] + buf[i]*fade_out[i] (two fp32 roundings, like the reference's
+    // in-place `*=` then `+=`), raw(i) = x[off+i]
+    auto val = [&](int i) {
+        const float v = x[off + i];
+        return i < sb ? __fadd_rn(__fmul_rn(v, fade_in[i]), __fmul_rn(bs[i], fade_out[i])) : v;
+    };
+    for (int i = threadIdx.x; i < block; i += 256) out[b * obs + i] = val(i);
+    for (int i = threadIdx.x; i < sb; i += 256) buf[i] = val(block + i);
+}
+
+extern "C" int svc_sola_stitch(const float* infer, long long infer_bstride, int infer_len, float* sola_buf,
+                               long long buf_bstride, const float* fade_in, const float* fade_out, float* out,
+                               long long out_bstride, int* offsets, int B, int sola_buffer_frame,
+                               int sola_search_frame, int block_frame, void* stream) {
+    const int sb = sola_buffer_frame, search = sola_search_frame;
+    if (B < 1 || sb < 1 || search < 0 || block_frame < 1 || infer == nullptr || sola_buf == nullptr ||
+        fade_in == nullptr || fade_out == nullptr || out == nullptr || offsets == nullptr ||
+        infer_len < search + block_frame + sb) {
+        svc_set_error("svc_sola_stitch: need infer_len >= search + block + sola_buffer_frame");
+        return SVC_ERR_ARG;
+    }
+    const int smem = (2 * sb + search) * 4;
+    if (smem > 200 * 1024) {
+        svc_set_error("svc_sola_stitch: window too large for shared memory");
+        return SVC_ERR_ARG;
+    }
+    static int attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+        cudaFuncSetAttribute(sola_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_smem = smem;
+    }
+    sola_stitch_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        infer, infer_bstride, sola_buf, buf_bstride, fade_in, fade_out, out, out_bstride, offsets, sb, search,
+        block_frame);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // error plumbing shared by all translation units
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";

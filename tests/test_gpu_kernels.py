@@ -351,3 +351,27 @@ def test_crossfade_stitch_bit_exact():
     waves[1, :40] = torch.from_numpy(z["xf_c2"]).cuda()
     out = ops.crossfade_stitch(waves, [64, 40], 64).cpu().numpy()
     assert np.array_equal(out, z["xf_out"])
+
+
+def test_sola_stitch_streams():
+    """svc_sola_stitch (all streams in one launch, state carried over ticks) vs the outputs of the REAL
+    reference lines (real-time-gui.py:1103-1137): same offsets, samples equal to fp32 round-off of the
+    correlation-independent arithmetic (the blend itself is bit-exact)."""
+    import json
+    import os
+
+    import numpy as np
+    import gen_golden_sola as gs
+    from seedvc_b200.streaming import SolaStitcher
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "sola_kat.npz"))
+    for name, m in json.loads(str(z["meta"])).items():
+        st = SolaStitcher(m["streams"], m["sb"], m["search"], m["block"])
+        for t in range(m["ticks"]):
+            x = torch.stack([gs.tick_input(name, s, t, m["n"]) for s in range(m["streams"])]).cuda()
+            out = st.step(x).cpu().numpy()
+            offs = st.offsets.cpu().numpy()
+            for s in range(m["streams"]):
+                assert int(offs[s]) == int(z[f"{name}_t{t}_s{s}_off"]), (name, t, s)
+                assert np.array_equal(out[s], z[f"{name}_t{t}_s{s}_out"]), (name, t, s)
+                assert np.array_equal(st.sola_buffer[s].cpu().numpy(), z[f"{name}_t{t}_s{s}_buf"])

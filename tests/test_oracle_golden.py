@@ -151,3 +151,27 @@ def test_mel_frontend_oracle_against_reference_golden():
         assert a.shape == b.shape == (n_mels, n_fft // 2 + 1)
         assert np.abs(a - b).max() < 1e-7 * max(1.0, np.abs(b).max())
         assert (a.sum(1) > 0).all()
+
+
+def test_sola_oracle_against_reference_golden():
+    """oracle.sola_step vs the REAL reference lines of real-time-gui.py (oracle/gen_golden_sola.py)."""
+    import json
+    import os
+
+    import numpy as np
+    import torch
+    import gen_golden_sola as gs
+    import seedvc_oracle as orc
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "sola_kat.npz"))
+    for name, m in json.loads(str(z["meta"])).items():
+        for s in range(m["streams"]):
+            st = gs.make_state(m["zc"], m["block"] // m["zc"], m["sb"] // m["zc"] if m["sb"] % m["zc"] == 0 else 2)
+            buf = torch.zeros(m["sb"])
+            for t in range(m["ticks"]):
+                x = gs.tick_input(name, s, t, m["n"])
+                out, buf, off = orc.sola_step(x, buf, st.fade_in_window, st.fade_out_window, m["sb"], m["search"],
+                                              m["block"])
+                assert off == int(z[f"{name}_t{t}_s{s}_off"])
+                assert np.array_equal(out.numpy(), z[f"{name}_t{t}_s{s}_out"])
+                assert np.array_equal(buf.numpy(), z[f"{name}_t{t}_s{s}_buf"])
