@@ -703,8 +703,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         constexpr bool direct = EPI >= 3;          // 3 direct, 4 direct pair, 5 direct with two outputs
         constexpr int acc_per_item = pair ? 64 : 32;   // accumulator columns per work item
         struct Item {
-            int it, ch, b, t_base, n0c, ncols;
+            int it, ch, b, t_base, n0c, ncols, step, n0;
             bool valid, last;
+        };
+        // RoPE items of a full tile are visited even chunks first, then odd ones: chunks 64 columns apart
+        // use the same 16 (cos, sin) pairs, so the table is read twice per tile instead of once per chunk
+        const bool rope_order = direct && !pair && p.epi.act == SVC_ACT_ROPE;
+        auto chunk_of = [&](int step, int ncols) {
+            const int n = ncols / acc_per_item;
+            if (!rope_order || ncols != BN || (n & 1)) return step;
+            return step < n / 2 ? 2 * step : 2 * (step - n / 2) + 1;
         };
         auto make_item = [&](int it, int ch) {          // full (re)computation: once per tile
             Item x;
@@ -712,25 +720,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             x.ch = ch;
             const int tile = blockIdx.x + it * gridDim.x;
             x.valid = tile < total_tiles;
-            x.b = 0, x.t_base = 0, x.n0c = 0, x.ncols = 0, x.last = true;
+            x.b = 0, x.t_base = 0, x.n0c = 0, x.ncols = 0, x.last = true, x.step = 0, x.n0 = 0;
             if (x.valid) {
                 const int n_tile = tile % p.n_tiles;
                 const int m_tile = tile / p.n_tiles;
                 x.b = m_tile / p.tiles_per_batch;
                 x.t_base = (m_tile - x.b * p.tiles_per_batch) * BM + lg * 32;
                 const int n0 = n_tile * BN;
+                x.n0 = n0;
                 x.ncols = min(BN, p.epi.N - n0);
-                x.n0c = n0 + ch * acc_per_item;
-                x.last = (ch + 1) * acc_per_item >= x.ncols;
+                x.step = 0;
+                x.ch = chunk_of(0, x.ncols);
+                x.n0c = n0 + x.ch * acc_per_item;
+                x.last = acc_per_item >= x.ncols;
             }
             return x;
         };
         auto next_item = [&](const Item& c) {           // within a tile: no divisions
             if (c.last) return make_item(c.it + 2, 0);
             Item x = c;
-            x.ch = c.ch + 1;
-            x.n0c = c.n0c + acc_per_item;
-            x.last = (x.ch + 1) * acc_per_item >= c.ncols;
+            x.step = c.step + 1;
+            x.ch = chunk_of(x.step, c.ncols);
+            x.n0c = c.n0 + x.ch * acc_per_item;
+            x.last = (x.step + 1) * acc_per_item >= c.ncols;
             return x;
         };
         // geometry used by the prefetch (4 columns per lane, 8 steps) in TMA mode
@@ -752,7 +764,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         const bool tr_on = (warp == 2 && lane == 0);
         while (cur.valid) {
             if (tr_on) GTRACE(0, tr_i, 0);
-            if (cur.ch == 0) {
+            if (cur.step == 0) {
                 mbar_wait(&tmem_full_bar[group], (cur.it >> 1) & 1);
                 tc_fence_after();
             }
@@ -764,8 +776,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             if constexpr (tma_mode) { g_nxt = g_tma; g_nxt.c0 = pair ? (nxt.n0c >> 1) : nxt.n0c; }
             if (nxt.valid && want_prefetch && g_nxt.vec && nxt.t_base < p.T && !(p.dbg & 32))
                 epi_prefetch(p.epi, g_nxt, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
-            if (rope_direct && nxt.valid && nxt.n0c < p.epi.rope_cols)
-                rope_prefetch_rows(p.epi, nxt.n0c, lane, nxt.t_base, rr_nxt);
+            if (rope_direct && nxt.valid && nxt.n0c < p.epi.rope_cols) {
+                const bool same = nxt.it == cur.it && cur.n0c < p.epi.rope_cols && ((nxt.n0c ^ cur.n0c) & 63) == 0;
+                if (same) {                 // same rows, same pair set: keep the table values
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rr_nxt[i] = rr_cur[i];
+                } else {
+                    rope_prefetch_rows(p.epi, nxt.n0c, lane, nxt.t_base, rr_nxt);
+                }
+            }
             if (res_direct && nxt.valid) res_prefetch_rows(p.epi, nxt.n0c, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
             if (tr_on) GTRACE(0, tr_i, 1);
             tc_wait_ld();
