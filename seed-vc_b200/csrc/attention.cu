@@ -48,6 +48,7 @@ struct alignas(64) AttnTcParams {
     long long o_bstride, o_rstride;
     const int* kv_len;
     int T, H;
+    int B, q_tiles, total_items;   // persistent grid: item = (b * H + h) * q_tiles + q_tile
     int dbg;       // SVC_DBG_ATTN: 1 = issue 1 of 8 PV MMAs, 2 = issue 1 of 4 QK^T MMAs (timing experiments)
 };
 
@@ -115,7 +116,9 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         : "memory");
 }
 
-// One CTA = AT_QT x 128 = 384 queries (three Q tiles) of one (batch, head); keys in blocks of 64.
+// Persistent kernel: one CTA per SM walks work items = AT_QT x 128 = 384 queries (three Q tiles) of one
+// (batch, head); keys in blocks of 64.  Ring stages and barrier parities continue across items (running
+// block counts), so the next item's loads and first S MMAs overlap the previous item's O read-out.
 //   warp 0    : TMA producer (Q tiles once, K_j / V_j through mbarrier rings shared by the tiles)
 //   warps 1-3 : one MMA-issuing thread per Q tile g: S_g = Q_g K_j^T (TMEM, 64 columns) and
 //               O_g += P_g V_j (TMEM, 64 columns, accumulated in place; A operand = P_g read
@@ -145,26 +148,31 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     uint64_t* s_empty = s_full + AT_QT;
     uint64_t* p_full = s_empty + AT_QT;
     uint64_t* p_empty = p_full + AT_QT;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + AT_QT);
+    uint64_t* q_empty = p_empty + AT_QT;    // 1: every tile's last S of the work item has retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * (AT_BM * AT_QT);
-    const int h = blockIdx.y;
-    const int b = blockIdx.z;
-    int kv_len = p.kv_len != nullptr ? p.kv_len[b] : p.T;
-    kv_len = max(1, min(kv_len, p.T));
-    const int n_blocks = (kv_len + AT_BN - 1) / AT_BN;
-#ifdef SVC_TRACE
-    const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
-                          (warp == 1 || warp == 4);
-#endif
-
+    // Persistent CTA: work items (q tile triple, head, batch entry) blockIdx.x, blockIdx.x + gridDim.x, ...
+    // Every role walks the same item sequence and keeps running block counts, so ring stages and barrier
+    // parities simply continue across items: the next item's Q / K / V loads and its first S MMAs overlap the
+    // previous item's O read-out, and TMEM / barriers are set up once per SM.
+    auto decode = [&](int item, int& q0, int& h, int& b, int& kv_len, int& n_blocks) {
+        const int qt = item % p.q_tiles;
+        const int bh = item / p.q_tiles;
+        h = bh % p.H;
+        b = bh / p.H;
+        q0 = qt * (AT_BM * AT_QT);
+        kv_len = p.kv_len != nullptr ? p.kv_len[b] : p.T;
+        kv_len = max(1, min(kv_len, p.T));
+        n_blocks = (kv_len + AT_BN - 1) / AT_BN;
+    };
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.qmap);
         tma_prefetch_desc(&p.kmap);
         tma_prefetch_desc(&p.vmap);
         mbar_init(q_full, 1);
+        mbar_init(q_empty, AT_QT);
         for (int i = 0; i < AT_KST; ++i) {
             mbar_init(&k_full[i], 1);
             mbar_init(&k_empty[i], AT_QT);
@@ -195,34 +203,25 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
     if (warp == 0) {
         reg_dealloc<40>();
         if (lane == 0) {
-            mbar_expect_tx(q_full, AT_QT * S::QTILE);
-            for (int g = 0; g < AT_QT; ++g)
-                tma_load_3d(smem + S::Q_OFF + g * S::QTILE, &p.qmap, q_full, h * AT_HD, q0 + g * AT_BM, b);
-            for (int j = 0; j < n_blocks; ++j) {
-                const int st = j % AT_KST;
-                const uint32_t ph = (j / AT_KST) & 1;
-                mbar_wait(&k_empty[st], ph ^ 1);
-#ifdef SVC_TRACE
-                if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) g_attn_trace[0][j][3] = clock64();
-#endif
-                mbar_expect_tx(&k_full[st], S::KTILE);
-                tma_load_3d(smem + S::K_OFF + st * S::KTILE, &p.kmap, &k_full[st], h * AT_HD,
-                            j * AT_BN, b);
-                mbar_wait(&v_empty[st], ph ^ 1);
-#ifdef SVC_TRACE
-                if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) g_attn_trace[0][j][4] = clock64();
-#endif
-                mbar_expect_tx(&v_full[st], S::KTILE);
-                tma_load_3d(smem + S::V_OFF + st * S::KTILE, &p.vmap, &v_full[st], h * AT_HD,
-                            j * AT_BN, b);
-#ifdef SVC_TRACE
-                if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 64) {
-                    while (!mbar_test_wait(&k_full[st], ph)) {}
-                    g_attn_trace[2][j][0] = clock64();      // K_j landed (producer view)
-                    while (!mbar_test_wait(&v_full[st], ph)) {}
-                    g_attn_trace[2][j][1] = clock64();      // V_j landed
+            int st = 0;
+            uint32_t ph = 0;
+            int ic = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++ic) {
+                int q0, h, b, kv_len, n_blocks;
+                decode(item, q0, h, b, kv_len, n_blocks);
+                mbar_wait(q_empty, (ic & 1) ^ 1);              // previous item's S MMAs no longer read Q
+                mbar_expect_tx(q_full, AT_QT * S::QTILE);
+                for (int g = 0; g < AT_QT; ++g)
+                    tma_load_3d(smem + S::Q_OFF + g * S::QTILE, &p.qmap, q_full, h * AT_HD, q0 + g * AT_BM, b);
+                for (int j = 0; j < n_blocks; ++j) {
+                    mbar_wait(&k_empty[st], ph ^ 1);
+                    mbar_expect_tx(&k_full[st], S::KTILE);
+                    tma_load_3d(smem + S::K_OFF + st * S::KTILE, &p.kmap, &k_full[st], h * AT_HD, j * AT_BN, b);
+                    mbar_wait(&v_empty[st], ph ^ 1);
+                    mbar_expect_tx(&v_full[st], S::KTILE);
+                    tma_load_3d(smem + S::V_OFF + st * S::KTILE, &p.vmap, &v_full[st], h * AT_HD, j * AT_BN, b);
+                    if (++st == AT_KST) st = 0, ph ^= 1;
                 }
-#endif
             }
         }
     } else if (warp >= 1 && warp <= AT_QT) {
@@ -240,7 +239,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         const uint32_t k_lo0 = desc_lo(smem_u32(smem + S::K_OFF));
         const uint32_t v_lo0 = desc_lo(smem_u32(smem + S::V_OFF), 1024);   // MN-major: LBO = 1024
         const uint32_t tS = tmem_S + g * AT_BN, tO = tmem_O + g * AT_HD, tP = tmem_P + g * (AT_BN / 2);
-        auto issue_s = [&](int st) {
+        auto issue_s = [&](int st, bool last_of_item) {
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t klo = k_lo0 + st * (S::KTILE >> 4);
@@ -249,6 +248,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                     tc_mma_f16_lh(tS, qlo + k * 2, kDescHiSw128, klo + k * 2, kDescHiSw128, idesc_s, k != 0);
                 tc_commit(&s_full[g]);
                 tc_commit(&k_empty[st]);
+                if (last_of_item) tc_commit(q_empty);
             }
             __syncwarp();
         };
@@ -265,22 +265,31 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             }
             __syncwarp();
         };
-        mbar_wait_warp(q_full, 0);
-        mbar_wait_warp(&k_full[0], 0);
-        issue_s(0);
-        int st_n = 1, ph_n = 0;          // ring stage / phase of block j + 1
-        int st_c = 0, ph_c = 0;          // ring stage / phase of block j
-        for (int j = 0; j < n_blocks; ++j) {
-            if (j + 1 < n_blocks) {
-                mbar_wait_warp(&k_full[st_n], ph_n);
-                mbar_wait_warp(&s_empty[g], j & 1);          // softmax g has S_g(j) in registers
-                issue_s(st_n);
-                if (++st_n == AT_KST) st_n = 0, ph_n ^= 1;
+        int st_s = 0, ph_s = 0;          // ring stage / phase of the next S to issue
+        int st_v = 0, ph_v = 0;          // ring stage / phase of the next PV to issue
+        uint32_t ns = 0;                 // S MMAs issued so far by this tile (global over items)
+        uint32_t npv = 0;                // PV MMAs issued so far
+        int ic = 0;
+        auto next_s = [&](bool last_of_item) {
+            mbar_wait_warp(&k_full[st_s], ph_s);
+            if (ns > 0) mbar_wait_warp(&s_empty[g], (ns - 1) & 1);     // softmax g holds S(ns-1) in registers
+            issue_s(st_s, last_of_item);
+            if (++st_s == AT_KST) st_s = 0, ph_s ^= 1;
+            ++ns;
+        };
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++ic) {
+            int q0, h, b, kv_len, n_blocks;
+            decode(item, q0, h, b, kv_len, n_blocks);
+            mbar_wait_warp(q_full, ic & 1);
+            next_s(n_blocks == 1);
+            for (int j = 0; j < n_blocks; ++j) {
+                if (j + 1 < n_blocks) next_s(j + 2 == n_blocks);
+                mbar_wait_warp(&v_full[st_v], ph_v);
+                mbar_wait_warp(&p_full[g], npv & 1);
+                issue_pv(st_v, j == 0);
+                if (++st_v == AT_KST) st_v = 0, ph_v ^= 1;
+                ++npv;
             }
-            mbar_wait_warp(&v_full[st_c], ph_c);
-            mbar_wait_warp(&p_full[g], j & 1);
-            issue_pv(st_c, j == 0);
-            if (++st_c == AT_KST) st_c = 0, ph_c ^= 1;
         }
     } else if (warp < 4) {
         reg_dealloc<40>();
@@ -297,13 +306,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         constexpr float kThresh = 8.0f;       // in log2 units
         const uint32_t tP = tmem_P + g * (AT_BN / 2) + lane_addr;
         float m_ref = 0.f, l_run = 0.f;       // m_ref in log2 units (already * log2e)
+        uint32_t nb = 0;                      // blocks this tile has processed so far (all items): barrier parities
+        int kv_len = 0, n_blocks = 0;
 
         // one KV block of this row; TAIL = the block holds keys >= kv_len (masked), only the last one
         auto block = [&](int j, auto tail_tag) {
             constexpr bool TAIL = decltype(tail_tag)::value;
-            TRACE(1, j, 0);
-            mbar_wait(&s_full[g], j & 1);
-            TRACE(1, j, 1);
+            mbar_wait(&s_full[g], nb & 1);
             tc_fence_after();
             constexpr int NC = AT_BN / 32;
             float s[NC][32];
@@ -312,11 +321,6 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
                 for (int c = 0; c < NC; ++c) tmem_ld_32x32(tS + c * 32, r[c]);
                 tc_wait_ld();
-                TRACE(1, j, 2);
-#ifdef SVC_TRACE
-                if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j < 64 && warp >= 6)
-                    g_attn_trace[2][j][warp - 4] = clock64();     // S load done, per softmax warp
-#endif
                 tc_fence_before();
                 mbar_arrive(&s_empty[g]);
                 const int kbase = j * AT_BN;
@@ -374,10 +378,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                 m_new = mx;
             }
             l_blk = exps(m_new);
-            TRACE(1, j, 3);
             // PV of the previous block must have retired before P / O are touched
-            mbar_wait(&p_empty[g], (j & 1) ^ 1);
-            TRACE(1, j, 4);
+            mbar_wait(&p_empty[g], (nb & 1) ^ 1);
             if (__any_sync(0xffffffffu, need)) {
                 tc_fence_after();
                 const float alpha = need ? fast_exp2(m_ref - m_new) : 1.0f;
@@ -400,37 +402,42 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             for (int c = 0; c < AT_BN / 64; ++c)
                 tmem_st_32x32(tP + c * 32, *reinterpret_cast<uint32_t (*)[32]>(&pk[c * 32]));
             tc_wait_st();
-            TRACE(1, j, 5);
             tc_fence_before();
             mbar_arrive(&p_full[g]);
-            TRACE(1, j, 6);
+            ++nb;
         };
-        for (int j = 0; j < n_blocks - 1; ++j) block(j, std::false_type{});
-        if (n_blocks * AT_BN > kv_len) block(n_blocks - 1, std::true_type{});
-        else block(n_blocks - 1, std::false_type{});
-        // last PV retired -> O complete
-        mbar_wait(&p_empty[g], (n_blocks - 1) & 1);
-        tc_fence_after();
-        const int t = q0 + g * AT_BM + row;
-        const float inv_l = 1.0f / l_run;
-        __nv_bfloat16* o = p.out + static_cast<long long>(b) * p.o_bstride +
-                           static_cast<long long>(t) * p.o_rstride + h * AT_HD;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int q0, h, b;
+            decode(item, q0, h, b, kv_len, n_blocks);
+            m_ref = 0.f, l_run = 0.f;
+            for (int j = 0; j < n_blocks - 1; ++j) block(j, std::false_type{});
+            if (n_blocks * AT_BN > kv_len) block(n_blocks - 1, std::true_type{});
+            else block(n_blocks - 1, std::false_type{});
+            // last PV of the item retired -> O complete
+            mbar_wait(&p_empty[g], (nb - 1) & 1);
+            tc_fence_after();
+            const int t = q0 + g * AT_BM + row;
+            const float inv_l = 1.0f / l_run;
+            __nv_bfloat16* o = p.out + static_cast<long long>(b) * p.o_bstride +
+                               static_cast<long long>(t) * p.o_rstride + h * AT_HD;
 #pragma unroll
-        for (int c = 0; c < AT_HD; c += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(tO + c, r);
-            tc_wait_ld();
-            if (t < p.T) {
+            for (int c = 0; c < AT_HD; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(tO + c, r);
+                tc_wait_ld();
+                if (t < p.T) {
 #pragma unroll
-                for (int d = 0; d < 32; d += 8) {
-                    uint4 q;
-                    q.x = pack_bf16(__uint_as_float(r[d]) * inv_l, __uint_as_float(r[d + 1]) * inv_l);
-                    q.y = pack_bf16(__uint_as_float(r[d + 2]) * inv_l, __uint_as_float(r[d + 3]) * inv_l);
-                    q.z = pack_bf16(__uint_as_float(r[d + 4]) * inv_l, __uint_as_float(r[d + 5]) * inv_l);
-                    q.w = pack_bf16(__uint_as_float(r[d + 6]) * inv_l, __uint_as_float(r[d + 7]) * inv_l);
-                    *reinterpret_cast<uint4*>(o + c + d) = q;
+                    for (int d = 0; d < 32; d += 8) {
+                        uint4 q;
+                        q.x = pack_bf16(__uint_as_float(r[d]) * inv_l, __uint_as_float(r[d + 1]) * inv_l);
+                        q.y = pack_bf16(__uint_as_float(r[d + 2]) * inv_l, __uint_as_float(r[d + 3]) * inv_l);
+                        q.z = pack_bf16(__uint_as_float(r[d + 4]) * inv_l, __uint_as_float(r[d + 5]) * inv_l);
+                        q.w = pack_bf16(__uint_as_float(r[d + 6]) * inv_l, __uint_as_float(r[d + 7]) * inv_l);
+                        *reinterpret_cast<uint4*>(o + c + d) = q;
+                    }
                 }
             }
+            tc_fence_before();        // the next item's first PV overwrites O: order it after these reads
         }
     }
     tc_fence_before();
@@ -543,7 +550,15 @@ extern "C" int svc_attention(const void* q, const void* k, const void* v, long l
                                  AttnSmem::TOTAL);
             attr_set = true;
         }
-        dim3 grid((T + AT_BM * AT_QT - 1) / (AT_BM * AT_QT), H, B);
+        p.B = B;
+        p.q_tiles = (T + AT_BM * AT_QT - 1) / (AT_BM * AT_QT);
+        const long long total = static_cast<long long>(p.q_tiles) * H * B;
+        if (total > 0x7fffffffLL) {
+            svc_set_error("svc_attention: too many work items");
+            return SVC_ERR_ARG;
+        }
+        p.total_items = static_cast<int>(total);
+        const int grid = p.total_items < 148 ? p.total_items : 148;     // one persistent CTA per SM
         attention_tc_kernel<<<grid, AT_THREADS, AttnSmem::TOTAL, st>>>(p);
         SVC_CHECK_LAUNCH();
         return SVC_OK;
