@@ -1006,6 +1006,7 @@ static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
 static bool flatten_batch(svc_gemm_desc& d, int* rope_mod) {
     *rope_mod = 0;
     static const int off = getenv("SVC_NO_FLATTEN") ? 1 : 0;
+    static const bool no_direct_path = getenv("SVC_NO_DIRECT") != nullptr || getenv("SVC_NO_TMA_STORE") != nullptr;
     if (off || d.B <= 1 || d.rowbias != nullptr || d.gate != nullptr) return false;
     const long long T = d.T;
     for (int s = 0; s < d.n_seg; ++s)
@@ -1020,7 +1021,7 @@ static bool flatten_batch(svc_gemm_desc& d, int* rope_mod) {
                                  reinterpret_cast<uintptr_t>(d.rope_tab_t) % 8 == 0 && d.out_op != nullptr &&
                                  d.out_f32 == nullptr && d.res == nullptr && !d.accumulate &&
                                  reinterpret_cast<uintptr_t>(d.out_op) % 16 == 0 && (d.oo_rstride * 2) % 16 == 0 &&
-                                 !getenv("SVC_NO_DIRECT") && !getenv("SVC_NO_TMA_STORE");
+                                 !no_direct_path;
         if (!direct_rope) return false;
         *rope_mod = d.T;
     }
@@ -1037,12 +1038,13 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
     const bool flattened = flatten_batch(d, &rope_mod);
     TcParams p;
     memset(&p, 0, sizeof(p));
+    static const bool bn96 = getenv("SVC_NO_BN96") == nullptr, bn192 = getenv("SVC_NO_BN192") == nullptr;
     int BN = 128;
     if (d.N <= 32) BN = 32;
     else if (d.N <= 64) BN = 64;
-    else if (d.N == 96 && !getenv("SVC_NO_BN96")) BN = 96;      // W box of exactly one tap's rows
+    else if (d.N == 96 && bn96) BN = 96;      // W box of exactly one tap's rows
     else if (d.N <= 128) BN = 128;
-    else if ((d.N == 192 || d.N == 384) && !getenv("SVC_NO_BN192")) BN = 192;   // exact tiles: no half-empty second tile / W box
+    else if ((d.N == 192 || d.N == 384) && bn192) BN = 192;   // exact tiles: no half-empty second tile / W box
     else BN = 256;
     // ---- A maps: one per distinct view ---------------------------------------------------
     struct AKey { const void* ptr; long long bs, rs; int rows, K; };
