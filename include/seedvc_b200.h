@@ -126,6 +126,13 @@ int svc_norm_mod(const float* x, long long x_bstride, long long x_rstride, const
                  const float* mul, const float* add, float eps, int mode, void* out,
                  long long o_bstride, long long o_rstride, int B, int T, int D, int out_dtype,
                  void* stream);
+/* Same, and additionally raw_out = x cast to the operand dtype (same strides as out): the U-ViT skip
+ * tensor / the operand copy of the hidden state (diffusion_transformer.py:133-141,185-186) falls out of
+ * the read the norm does anyway, so the producing GEMM needs only its fp32 output. */
+int svc_norm_mod_copy(const float* x, long long x_bstride, long long x_rstride, const float* gamma,
+                      const float* mul, const float* add, float eps, int mode, void* out, void* raw_out,
+                      long long o_bstride, long long o_rstride, int B, int T, int D, int out_dtype,
+                      void* stream);
 
 /* ---------------------------------------------------------------------------
  * svc_snake_aa: anti-aliased Snake / SnakeBeta = 2x Kaiser-sinc FIR upsample, x + sin^2(a x)/b,

@@ -46,6 +46,8 @@ SIGNATURES = {
                       c_int, c_int, c_vp],
     "svc_norm_mod": [c_vp, c_ll, c_ll, c_vp, c_vp, c_vp, c_float, c_int, c_vp, c_ll, c_ll, c_int,
                      c_int, c_int, c_int, c_vp],
+    "svc_norm_mod_copy": [c_vp, c_ll, c_ll, c_vp, c_vp, c_vp, c_float, c_int, c_vp, c_vp, c_ll, c_ll, c_int,
+                          c_int, c_int, c_int, c_vp],
     "svc_snake_aa": [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "svc_snake_conv_post": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_vp],

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) norm_mod_kernel(
     const float* __restrict__ x, long long x_bstride, long long x_rstride,
     const float* __restrict__ gamma, const float* __restrict__ mul, const float* __restrict__ add,
     float eps, int mode, TO* __restrict__ out, long long o_bstride, long long o_rstride, int B, int T,
-    int D) {
+    int D, TO* __restrict__ raw) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= B * T) return;
@@ -81,6 +81,17 @@ __global__ void __launch_bounds__(256) norm_mod_kernel(
                 q.x = pack_bf16(y[0], y[1]);
                 q.y = pack_bf16(y[2], y[3]);
                 *reinterpret_cast<uint2*>(orow + c) = q;
+            }
+            if (raw != nullptr) {      // un-normalised copy of the row in the operand dtype (same layout as out)
+                TO* rrow = raw + static_cast<long long>(b) * o_bstride + static_cast<long long>(t) * o_rstride;
+                if constexpr (sizeof(TO) == 4) {
+                    *reinterpret_cast<float4*>(rrow + c) = v[i];
+                } else {
+                    uint2 q;
+                    q.x = pack_bf16(v[i].x, v[i].y);
+                    q.y = pack_bf16(v[i].z, v[i].w);
+                    *reinterpret_cast<uint2*>(rrow + c) = q;
+                }
             }
         }
     }
@@ -232,10 +243,10 @@ static inline bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>
 
 using namespace svc;
 
-extern "C" int svc_norm_mod(const float* x, long long x_bstride, long long x_rstride,
+static int norm_mod_impl(const float* x, long long x_bstride, long long x_rstride,
                             const float* gamma, const float* mul, const float* add, float eps,
                             int mode, void* out, long long o_bstride, long long o_rstride, int B,
-                            int T, int D, int out_dtype, void* stream) {
+                            int T, int D, int out_dtype, void* stream, void* raw_out) {
     if (D % 4 != 0 || D > 2048 || B < 1 || T < 1) {
         svc_set_error("svc_norm_mod: D must be a multiple of 4 and <= 2048");
         return SVC_ERR_ARG;
@@ -253,7 +264,8 @@ extern "C" int svc_norm_mod(const float* x, long long x_bstride, long long x_rst
 #define LAUNCH_NORM(TO, MAXV)                                                                   \
     norm_mod_kernel<TO, MAXV><<<blocks, 256, 0, st>>>(x, x_bstride, x_rstride, gamma, mul, add, \
                                                       eps, mode, static_cast<TO*>(out),         \
-                                                      o_bstride, o_rstride, B, T, D)
+                                                      o_bstride, o_rstride, B, T, D,             \
+                                                      static_cast<TO*>(raw_out))
     if (out_dtype == SVC_F32) {
         if (D <= 512) LAUNCH_NORM(float, 4);
         else if (D <= 1024) LAUNCH_NORM(float, 8);
@@ -266,6 +278,22 @@ extern "C" int svc_norm_mod(const float* x, long long x_bstride, long long x_rst
 #undef LAUNCH_NORM
     SVC_CHECK_LAUNCH();
     return SVC_OK;
+}
+
+extern "C" int svc_norm_mod(const float* x, long long x_bstride, long long x_rstride, const float* gamma,
+                            const float* mul, const float* add, float eps, int mode, void* out,
+                            long long o_bstride, long long o_rstride, int B, int T, int D, int out_dtype,
+                            void* stream) {
+    return norm_mod_impl(x, x_bstride, x_rstride, gamma, mul, add, eps, mode, out, o_bstride, o_rstride, B, T, D,
+                         out_dtype, stream, nullptr);
+}
+
+extern "C" int svc_norm_mod_copy(const float* x, long long x_bstride, long long x_rstride, const float* gamma,
+                                 const float* mul, const float* add, float eps, int mode, void* out,
+                                 void* raw_out, long long o_bstride, long long o_rstride, int B, int T, int D,
+                                 int out_dtype, void* stream) {
+    return norm_mod_impl(x, x_bstride, x_rstride, gamma, mul, add, eps, mode, out, o_bstride, o_rstride, B, T, D,
+                         out_dtype, stream, raw_out);
 }
 
 extern "C" int svc_cfg_euler(float* x, const float* v, int n_branch, float c0, float c1, float c2,

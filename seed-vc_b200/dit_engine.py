@@ -425,6 +425,7 @@ class DiTEngine:
         recv = set(range(L // 2 + 1, L)) if sp.uvit else set()
         skips = []
         skip_bufs = list(st["skips"])
+        pending_raw = None        # skip tensor of the previous (emit) layer: written by this layer's first norm
         for i in range(L):
             lw = w["layers"][i]
             if i in recv:
@@ -433,11 +434,14 @@ class DiTEngine:
                          B=R, T=Tq, bias=lw["skip_b"], out_f32=h)
             # ---- attention --------------------------------------------------------------
             if sp.version == 1:
+                # the operand copy of an emit layer's output (the U-ViT skip tensor) falls out of this norm's
+                # read of h, so that layer's w2 GEMM needs only its fp32 output
                 if sp.time_as_token:
-                    ops.norm_mod(h, xn, gamma=lw["g_attn"])
+                    ops.norm_mod(h, xn, gamma=lw["g_attn"], raw_out=pending_raw)
                 else:
                     a = self._ada(s, f"attn{i}")
-                    ops.norm_mod(h, xn, gamma=lw["g_attn"], mul=a[:D], add=a[D:])
+                    ops.norm_mod(h, xn, gamma=lw["g_attn"], mul=a[:D], add=a[D:], raw_out=pending_raw)
+                pending_raw = None
                 gate_a = gate_m = None
             else:
                 a = self._ada(s, f"blk{i}")     # shift, 1+scale, gate, shift, 1+scale, gate
@@ -458,7 +462,10 @@ class DiTEngine:
                 ops.norm_mod(h, xn, gamma=lw["g_ffn"], mul=a[4 * D:5 * D], add=a[3 * D:4 * D])
             ops.gemm([(xn, 0, lw["w13"])], 2 * sp.I, B=R, T=Tq, act=ACT_SWIGLU_PAIR, out_op=ff)
             out_op = None
-            if i in emit:
+            if i in emit and sp.version == 1 and (i + 1) < L and (i + 1) not in recv:
+                pending_raw = skip_bufs.pop(0)       # filled by layer i+1's attention norm
+                skips.append(pending_raw)
+            elif i in emit:
                 out_op = skip_bufs.pop(0)
                 skips.append(out_op)
             elif (i + 1) in recv:

@@ -176,19 +176,28 @@ class Ops:
         self._t1()
 
     # ------------------------------------------------------------------ norms
-    def norm_mod(self, x, out, *, gamma=None, mul=None, add=None, eps=1e-5, mode=0):
-        """out = norm(x) * gamma * mul + add; mode 0 RMSNorm, 1 LayerNorm(no affine)."""
-        self._chk(x, out, gamma, mul, add)
+    def norm_mod(self, x, out, *, gamma=None, mul=None, add=None, eps=1e-5, mode=0, raw_out=None):
+        """out = norm(x) * gamma * mul + add; mode 0 RMSNorm, 1 LayerNorm(no affine).
+        ``raw_out`` (same shape / dtype / strides as out): also store the un-normalised rows (operand copy)."""
+        self._chk(x, out, gamma, mul, add, raw_out)
         B, T, D = x.shape
         assert x.dtype == torch.float32 and x.stride(2) == 1 and out.shape == x.shape
         assert out.stride(2) == 1
         for v in (gamma, mul, add):
             assert v is None or (v.dtype == torch.float32 and v.numel() == D and v.is_contiguous())
-        self._t0("norm_mod", 0.0, float(B) * T * D * (4 + out.element_size()))
-        check(self.lib.svc_norm_mod(x.data_ptr(), x.stride(0), x.stride(1), _ptr(gamma), _ptr(mul),
-                                    _ptr(add), float(eps), mode, out.data_ptr(), out.stride(0),
-                                    out.stride(1), B, T, D, self._code(out.dtype), self._stream()),
-              "svc_norm_mod")
+        nbytes = float(B) * T * D * (4 + out.element_size() * (2 if raw_out is not None else 1))
+        self._t0("norm_mod", 0.0, nbytes)
+        if raw_out is None:
+            check(self.lib.svc_norm_mod(x.data_ptr(), x.stride(0), x.stride(1), _ptr(gamma), _ptr(mul),
+                                        _ptr(add), float(eps), mode, out.data_ptr(), out.stride(0),
+                                        out.stride(1), B, T, D, self._code(out.dtype), self._stream()),
+                  "svc_norm_mod")
+        else:
+            assert raw_out.shape == out.shape and raw_out.dtype == out.dtype and raw_out.stride() == out.stride()
+            check(self.lib.svc_norm_mod_copy(x.data_ptr(), x.stride(0), x.stride(1), _ptr(gamma), _ptr(mul),
+                                             _ptr(add), float(eps), mode, out.data_ptr(), raw_out.data_ptr(),
+                                             out.stride(0), out.stride(1), B, T, D, self._code(out.dtype),
+                                             self._stream()), "svc_norm_mod_copy")
         self._t1()
 
     # ------------------------------------------------------------------ BigVGAN activations

@@ -86,8 +86,10 @@ class EmuOps:
         y = torch.softmax(s, -1) @ v
         out.copy_(y.transpose(1, 2).reshape(B, T, D))
 
-    def norm_mod(self, x, out, *, gamma=None, mul=None, add=None, eps=1e-5, mode=0):
+    def norm_mod(self, x, out, *, gamma=None, mul=None, add=None, eps=1e-5, mode=0, raw_out=None):
         self.launches += 1
+        if raw_out is not None:
+            raw_out.copy_(x)
         if mode == 0:
             y = x * torch.rsqrt(torch.mean(x * x, -1, keepdim=True) + eps)
         else:

@@ -218,6 +218,12 @@ def test_norm_mod(D, mode):
         emu.norm_mod(x, ref, **kw)
         e = rel_l2(out.float(), ref)
         assert e < (1e-5 if mode == "fp32" else 4e-3)
+        # svc_norm_mod_copy: same result + the un-normalised rows in the operand dtype
+        out2 = torch.zeros_like(out)
+        raw = torch.zeros_like(out)
+        ops.norm_mod(x, out2, raw_out=raw, **kw)
+        assert torch.equal(out2, out)
+        assert torch.equal(raw, x.to(ops.op_dtype))
 
 
 @pytest.mark.parametrize("C,L", [(24, 1000), (48, 515), (96, 300), (768, 70), (192, 129), (16, 40),
