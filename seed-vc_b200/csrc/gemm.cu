@@ -1007,7 +1007,9 @@ static bool flatten_batch(svc_gemm_desc& d, int* rope_mod) {
     *rope_mod = 0;
     static const int off = getenv("SVC_NO_FLATTEN") ? 1 : 0;
     static const bool no_direct_path = getenv("SVC_NO_DIRECT") != nullptr || getenv("SVC_NO_TMA_STORE") != nullptr;
-    if (off || d.B <= 1 || d.rowbias != nullptr || d.gate != nullptr) return false;
+    if (off || d.B <= 1) return false;
+    // per-batch-entry vectors are fine when every entry uses the same one (stride 0: v2 AdaLN gates)
+    if ((d.rowbias != nullptr && d.rowbias_bstride != 0) || (d.gate != nullptr && d.gate_bstride != 0)) return false;
     const long long T = d.T;
     for (int s = 0; s < d.n_seg; ++s)
         if (d.a_shift[s] != 0 || d.a_rows[s] != d.T || d.a_bstride[s] != T * d.a_rstride[s]) return false;
