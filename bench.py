@@ -187,6 +187,7 @@ def run_ours(a):
     from seedvc_b200 import configs, synth
     from seedvc_b200.bigvgan import BigVGAN
     from seedvc_b200.flow_matching import CFM
+    from seedvc_b200.sharding import barrier as shard_barrier, max_over_ranks, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,7 +209,9 @@ def run_ours(a):
     gen = T - Tp
 
     # synthetic utterances of this rank (ids offset by rank): host pinned + device resident copies
-    mu, prompt, style, z = synth.synth_batch(B, T, Tp, C, cd, first_id=rank * B)
+    first_utt, n_utt = shard_range(world * B, world, rank)        # contiguous shard of the utterance list
+    assert n_utt == B
+    mu, prompt, style, z = synth.synth_batch(B, T, Tp, C, cd, first_id=first_utt)
     host = [t.pin_memory() for t in (mu, prompt, style, z)]
     lens_h = torch.full((B,), T, dtype=torch.int64).pin_memory()
     wav_h = torch.empty(B, 1, gen * hop, dtype=torch.float32).pin_memory()
@@ -231,10 +234,7 @@ def run_ours(a):
         return wav
 
     def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        shard_barrier(dev)
 
     def timed(fn, k):
         barrier()
@@ -244,10 +244,7 @@ def run_ours(a):
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return max_over_ranks(e0.elapsed_time(e1), dev)
 
     ops_d, ops_v = cfm.estimator.engine().ops, voc._prepare()["ops"]
     for _ in range(max(a.warmup, 1)):
