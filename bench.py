@@ -28,6 +28,8 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+_JSON_OUT = None      # real stdout when fd 1 has been redirected (multi-rank runs)
+
 WORKLOADS = {
     # name: (v1 model, vocoder, B per GPU, T, Tp, Euler steps, cfg)
     "config2": ("whisper_small", "bigvgan_22k", 32, 2580, 430, 25, 0.7),
@@ -195,7 +197,12 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SVC_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL_DEBUG is left to the caller / driver.  NCCL logs to fd 1, so fd 1 is pointed at stderr for the
+        # life of the process and the one JSON line goes to a saved copy of the real stdout.
+        global _JSON_OUT
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     model, vocn, B, T, Tp, n_steps, cfg = WORKLOADS[a.workload]
     if a.batch:
@@ -334,7 +341,7 @@ def run_ours(a):
         "cpu_baseline": cpu,
         "kernel_breakdown": breakdown,
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_JSON_OUT or sys.stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

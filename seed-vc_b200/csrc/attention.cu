@@ -49,7 +49,6 @@ struct alignas(64) AttnTcParams {
     const int* kv_len;
     int T, H;
     int B, q_tiles, total_items;   // persistent grid: item = (b * H + h) * q_tiles + q_tile
-    int dbg;       // SVC_DBG_ATTN: 1 = issue 1 of 8 PV MMAs, 2 = issue 1 of 4 QK^T MMAs (timing experiments)
 };
 
 struct AttnSmem {
@@ -542,8 +541,6 @@ extern "C" int svc_attention(const void* q, const void* k, const void* v, long l
         p.kv_len = kv_len;
         p.T = T;
         p.H = H;
-        static const int dbg = getenv("SVC_DBG_ATTN") ? atoi(getenv("SVC_DBG_ATTN")) : 0;
-        p.dbg = dbg;
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

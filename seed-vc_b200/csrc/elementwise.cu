@@ -204,16 +204,21 @@ __global__ void reflect_halo_kernel(TO* __restrict__ buf, long long bstride, lon
     int len = lens != nullptr ? lens[b] : T;
     len = max(2, min(len, T));
     TO* base = buf + static_cast<long long>(b) * bstride;
-    int dst, src;
+    // source = a BODY row, index reflected inside [0, len-1] (never a halo row another block of this launch
+    // is writing, whatever len is; for len > pad this is exactly torch's reflect padding)
+    int dst, j;
     if (i < pad) {
         dst = pad - 1 - i;          // left halo row
-        src = pad + (i + 1);        // body row i+1
+        j = i + 1;                  // body row i+1
+        if (j > len - 1) j = 2 * (len - 1) - j;
     } else {
         const int k = i - pad;
         dst = pad + len + k;        // right halo row
-        src = pad + (len - 2 - k);  // body row len-2-k
+        j = len - 2 - k;            // body row len-2-k
+        if (j < 0) j = -j;
     }
-    src = max(src, 0);
+    j = min(max(j, 0), len - 1);
+    const int src = pad + j;
     for (int c = threadIdx.x; c < C; c += blockDim.x)
         base[static_cast<long long>(dst) * rstride + c] = base[static_cast<long long>(src) * rstride + c];
 }
@@ -692,6 +697,15 @@ __global__ void __launch_bounds__(256) sola_stitch_kernel(const float* __restric
     for (int i = threadIdx.x; i < sb + search; i += 256) xs[i] = x[i];
     for (int i = threadIdx.x; i < sb; i += 256) bs[i] = buf[i];
     __syncthreads();
+    // argmax with torch.argmax semantics: NaN ranks above every number (the first NaN wins), ties go to the
+    // smallest offset.  Threads without a candidate carry offset INT_MAX and lose every comparison; the final
+    // offset is clamped to [0, search] so a non-finite input can never index outside the window.
+    auto better = [](float v2, int o2, float v1, int o1) {
+        const bool n2 = v2 != v2, n1 = v1 != v1;
+        if (n2 != n1) return n2;
+        if (n2 || v2 == v1) return o2 < o1;
+        return v2 > v1;
+    };
     float bv = -INFINITY;
     int bo = 0x7fffffff;
     for (int o = threadIdx.x; o <= search; o += 256) {
@@ -702,21 +716,22 @@ __global__ void __launch_bounds__(256) sola_stitch_kernel(const float* __restric
             den = fmaf(v, v, den);
         }
         const float c = nom / sqrtf(den + 1e-8f);
-        if (c > bv) bv = c, bo = o;                   // first maximum within this thread's offsets
+        if (bo == 0x7fffffff || better(c, o, bv, bo)) bv = c, bo = o;
     }
     best_v[threadIdx.x] = bv;
     best_o[threadIdx.x] = bo;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {               // argmax, ties -> smallest offset (torch.argmax)
+    for (int s = 128; s > 0; s >>= 1) {
         if (threadIdx.x < s) {
             const float v2 = best_v[threadIdx.x + s];
             const int o2 = best_o[threadIdx.x + s];
-            if (v2 > best_v[threadIdx.x] || (v2 == best_v[threadIdx.x] && o2 < best_o[threadIdx.x]))
+            if (o2 != 0x7fffffff &&
+                (best_o[threadIdx.x] == 0x7fffffff || better(v2, o2, best_v[threadIdx.x], best_o[threadIdx.x])))
                 best_v[threadIdx.x] = v2, best_o[threadIdx.x] = o2;
         }
         __syncthreads();
     }
-    const int off = best_o[0];
+    const int off = min(max(best_o[0], 0), search);
     if (threadIdx.x == 0) offsets[b] = off;
     // faded(i) = x[off+i]*fade_in[i] + buf[i]*fade_out[i] (two fp32 roundings, like the reference's
     // in-place `*=` then `+=`), raw(i) = x[off+i]

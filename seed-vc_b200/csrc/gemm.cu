@@ -40,7 +40,9 @@ struct alignas(64) TcParams {
     TcSeg seg[SVC_MAX_SEG];
     int n_seg, total_kb;
     int B, T, tiles_per_batch, n_tiles;
-    int dbg;   // SVC_DBG env: 1 = skip epilogue body, 2 = skip MMA issue (profiling experiments)
+#ifdef SVC_TRACE
+    int dbg;   // trace builds only (SVC_DBG env): 1 = skip epilogue body, 2 = skip MMA issue (timing experiments)
+#endif
     // TMA-store epilogue: 0 = off (register/LSU epilogue), 1 = bf16 tile -> out_op,
     // 2 = fp32 tile reduce-added into out_f32 (in-place residual), 3 = fp32 tile -> out_f32
     int store_mode;
@@ -51,6 +53,16 @@ struct alignas(64) TcParams {
     CUtensorMap omap;          // (N_out, T, B) view of the output, box {32, 32, 1}; swizzled when direct
     EpiParams epi;
 };
+
+// Work-skipping / path-forcing experiment switches exist only in -DSVC_TRACE builds
+// (libseedvc_b200_trace.so, never shipped): the product library does not read the environment.
+#ifdef SVC_TRACE
+#define SVC_DBG_BITS(p) ((p).dbg)
+static bool svc_env_flag(const char* name) { return getenv(name) != nullptr; }
+#else
+#define SVC_DBG_BITS(p) 0
+static constexpr bool svc_env_flag(const char*) { return false; }
+#endif
 
 #ifdef SVC_TRACE
 __device__ long long g_gemm_trace[2][128][8];   // [0]: epilogue warp 2 lane 0 per item, [1]: MMA thread per tile
@@ -671,7 +683,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     tc_fence_after();
                     const uint32_t alo = a_lo0 + stage * (S::STAGE_BYTES >> 4);
                     const uint32_t blo = alo + (S::A_BYTES >> 4);
-                    if (!(p.dbg & 2)) {
+                    if (!(SVC_DBG_BITS(p) & 2)) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             tc_mma_f16_lh(d_tmem, alo + k * 2, kDescHiSw128, blo + k * 2, kDescHiSw128,
@@ -774,7 +786,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             const Item nxt = next_item(cur);
             EpiChunk g_nxt = epi_chunk_geom(p.epi, nxt.n0c);
             if constexpr (tma_mode) { g_nxt = g_tma; g_nxt.c0 = pair ? (nxt.n0c >> 1) : nxt.n0c; }
-            if (nxt.valid && want_prefetch && g_nxt.vec && nxt.t_base < p.T && !(p.dbg & 32))
+            if (nxt.valid && want_prefetch && g_nxt.vec && nxt.t_base < p.T && !(SVC_DBG_BITS(p) & 32))
                 epi_prefetch(p.epi, g_nxt, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
             if (rope_direct && nxt.valid && nxt.n0c < p.epi.rope_cols) {
                 const bool same = nxt.it == cur.it && cur.n0c < p.epi.rope_cols && ((nxt.n0c ^ cur.n0c) & 63) == 0;
@@ -794,13 +806,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
             }
-            if (cur.t_base < p.T && !(p.dbg & 1)) {
+            if (cur.t_base < p.T && !(SVC_DBG_BITS(p) & 1)) {
                 if constexpr (EPI == 0) {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     epilogue_chunk_coalesced(p.epi, g_cur, stage_buf, lane, cur.b, cur.t_base, p.T,
-                                             cur.n0c, v, rr_cur, p.dbg);
+                                             cur.n0c, v, rr_cur, SVC_DBG_BITS(p));
                 } else if constexpr (pair) {
                     float v[64];
 #pragma unroll
@@ -1005,8 +1017,8 @@ static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
 // 128-row tile grid per batch entry (21 tiles for 20.16); flattened, config 2 runs 1291 tiles instead of 1344.
 static bool flatten_batch(svc_gemm_desc& d, int* rope_mod) {
     *rope_mod = 0;
-    static const int off = getenv("SVC_NO_FLATTEN") ? 1 : 0;
-    static const bool no_direct_path = getenv("SVC_NO_DIRECT") != nullptr || getenv("SVC_NO_TMA_STORE") != nullptr;
+    static const int off = svc_env_flag("SVC_NO_FLATTEN") ? 1 : 0;
+    static const bool no_direct_path = svc_env_flag("SVC_NO_DIRECT") || svc_env_flag("SVC_NO_TMA_STORE");
     if (off || d.B <= 1) return false;
     // per-batch-entry vectors are fine when every entry uses the same one (stride 0: v2 AdaLN gates)
     if ((d.rowbias != nullptr && d.rowbias_bstride != 0) || (d.gate != nullptr && d.gate_bstride != 0)) return false;
@@ -1040,7 +1052,7 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
     const bool flattened = flatten_batch(d, &rope_mod);
     TcParams p;
     memset(&p, 0, sizeof(p));
-    static const bool bn96 = getenv("SVC_NO_BN96") == nullptr, bn192 = getenv("SVC_NO_BN192") == nullptr;
+    static const bool bn96 = !svc_env_flag("SVC_NO_BN96"), bn192 = !svc_env_flag("SVC_NO_BN192");
     int BN = 128;
     if (d.N <= 32) BN = 32;
     else if (d.N <= 64) BN = 64;
@@ -1074,8 +1086,10 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
         const char* wp = static_cast<const char*>(d.w_ptr[s]);
         for (int i = 0; i < n_w; ++i) {
             const long long rb = wkeys[i].rs * 2;
+            // merge only slices that start inside or directly behind the rows this map already covers (taps of
+            // one (k, N, K) weight): two separately allocated weights never share a map by address coincidence
             if (wkeys[i].rs == d.w_rstride[s] && wkeys[i].K == d.K[s] && wp >= wkeys[i].base &&
-                (wp - wkeys[i].base) % rb == 0 && (wp - wkeys[i].base) / rb < (1 << 24)) {
+                (wp - wkeys[i].base) % rb == 0 && (wp - wkeys[i].base) / rb <= wkeys[i].rows) {
                 wi = i;
                 row0 = (wp - wkeys[i].base) / rb;
             }
@@ -1100,8 +1114,10 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
             return SVC_ERR_ARG;
         }
     }
+#ifdef SVC_TRACE
     static const int dbg = getenv("SVC_DBG") ? atoi(getenv("SVC_DBG")) : 0;
     p.dbg = dbg;
+#endif
     p.n_seg = d.n_seg;
     p.total_kb = total_kb;
     p.B = d.B;
@@ -1111,8 +1127,8 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
     p.epi = make_epi_params(d);
     p.epi.rope_mod = rope_mod;
     // ---- TMA-store epilogue when the output pattern allows it ------------------------------
-    static const int no_tma_store = getenv("SVC_NO_TMA_STORE") ? 1 : 0;
-    static const int no_direct = getenv("SVC_NO_DIRECT") ? 1 : 0;
+    static const int no_tma_store = svc_env_flag("SVC_NO_TMA_STORE") ? 1 : 0;
+    static const int no_direct = svc_env_flag("SVC_NO_DIRECT") ? 1 : 0;
     p.store_mode = 0;
     // row-layout epilogue (no transpose); RoPE needs the pair-major table
     p.direct = !no_direct && d.N % 4 == 0 &&

@@ -90,7 +90,10 @@ class InterpolateRegulator(nn.Module):
 
     def _prepare(self):
         dev = self.mask_token.device
-        key = (self.mode, str(dev))
+        # like DiT.engine() / BigVGAN._prepare(): any parameter update (in-place write, a parent module's
+        # load_state_dict, .to()) changes _version or data_ptr and rebuilds the kernel-side weights
+        key = (self.mode, str(dev), tuple(p._version for p in self.parameters()),
+               tuple(p.data_ptr() for p in self.parameters()))
         if self._prep is not None and self._prep["key"] == key:
             return self._prep
         ops = Ops(self.mode)

@@ -381,3 +381,40 @@ def test_sola_stitch_streams():
                 assert int(offs[s]) == int(z[f"{name}_t{t}_s{s}_off"]), (name, t, s)
                 assert np.array_equal(out[s], z[f"{name}_t{t}_s{s}_out"]), (name, t, s)
                 assert np.array_equal(st.sola_buffer[s].cpu().numpy(), z[f"{name}_t{t}_s{s}_buf"])
+
+
+def test_sola_stitch_non_finite_inputs():
+    """A NaN / Inf sample in the new block or in the kept tail must not fault: the offset stays
+    inside [0, search]; torch.argmax semantics (NaN ranks highest, first one wins) are kept."""
+    from seedvc_b200.streaming import SolaStitcher
+
+    sb, search, block = 64, 32, 256
+    n = search + block + sb
+    g = torch.Generator().manual_seed(9)
+    for where in ("infer_nan", "infer_inf", "buffer_nan", "all_nan"):
+        st = SolaStitcher(3, sb, search, block)
+        st.sola_buffer.copy_(torch.randn(3, sb, generator=g))
+        x = torch.randn(3, n, generator=g)
+        if where == "infer_nan":
+            x[1, 40] = float("nan")
+        elif where == "infer_inf":
+            x[1, 40] = float("inf")
+        elif where == "buffer_nan":
+            st.sola_buffer[1, 5] = float("nan")
+        else:
+            x[1] = float("nan")
+        buf0 = st.sola_buffer.clone().cpu()
+        out = st.step(x.cuda())
+        torch.cuda.synchronize()
+        offs = st.offsets.cpu()
+        assert int(offs.min()) >= 0 and int(offs.max()) <= search, (where, offs)
+        # reference lines (real-time-gui.py:1103-1113) on the same stream
+        for s in range(3):
+            xs = x[s, :sb + search][None, None]
+            cor_nom = torch.nn.functional.conv1d(xs, buf0[s][None, None])
+            cor_den = torch.sqrt(torch.nn.functional.conv1d(xs ** 2, torch.ones(1, 1, sb)) + 1e-8)
+            c = cor_nom[0, 0] / cor_den[0, 0]
+            if not torch.isnan(c).any():
+                continue       # finite streams are covered bit-exactly by test_sola_stitch_streams
+            assert int(offs[s]) == int(torch.argmax(c)), (where, s, int(offs[s]), int(torch.argmax(c)))
+        assert out.shape == (3, block)
