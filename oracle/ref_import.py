@@ -18,10 +18,21 @@ import sys
 import types
 
 REF_ROOT = os.environ.get("SEEDVC_REFERENCE", "/root/reference")
+# staged copy of the hot-path files (oracle/build_ref.py): what the GPU box has instead of /root/reference
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+if not os.path.isdir(os.path.join(REF_ROOT, "modules")) and os.path.isdir(os.path.join(STAGED_ROOT, "modules")):
+    REF_ROOT = STAGED_ROOT
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "modules"))
+
+
+def kind() -> str:
+    """'reference' (full tree), 'oracle/_ref' (staged copy) or 'none'."""
+    if not available():
+        return "none"
+    return "oracle/_ref" if os.path.abspath(REF_ROOT) == os.path.abspath(STAGED_ROOT) else "reference"
 
 
 def _install_stubs():

@@ -260,11 +260,14 @@ class BASECFM(nn.Module):
 
     @torch.no_grad()
     def solve_euler(self, x, x_lens, prompt, mu, style, f0, t_span, inference_cfg_rate=0.5, *,
-                    t_values_dev=None):
+                    t_values_dev=None, step_hook=None):
         """Fixed-step Euler with batched CFG.  Reference: modules/flow_matching.py:55-112.
 
         ``t_values_dev`` (keyword only, used by graphs.GraphedConversion): the per-step times already on
         the device, so that no host-to-device copy happens inside a CUDA-graph capture.
+        ``step_hook(s, v)`` (keyword only, parity tests): called after every Euler step with the CFG-combined
+        velocity ``v`` (B, T, C) fp32 that step integrated (costs an extra torch op per step; product callers
+        leave it None).
 
         x: (B, C, T) noise; prompt: (B, C, Tp); mu: (B, T, content_dim); style: (B, 192);
         ``f0`` is accepted and ignored like in the reference (App. D-3)."""
@@ -304,6 +307,8 @@ class BASECFM(nn.Module):
                        torch.stack(t_vals) if t_values_dev is None else t_values_dev)
         for s in range(len(dts)):
             v = eng.step(s, x_op)
+            if step_hook is not None:
+                step_hook(s, sum(c * v[k * B:(k + 1) * B] for k, c in enumerate(coefs)))
             ops.cfg_euler(xs, v, coefs, dts[s], Tp, st["x_lens"], x_op)
         out = torch.empty(B, C, T, dtype=torch.float32, device=dev)
         ops.btc_to_bct(xs, out)

@@ -148,7 +148,7 @@ class CFM(nn.Module):
 
     @torch.no_grad()
     def solve_euler(self, x, x_lens, prompt, mu, style, t_span, inference_cfg_rate=[0.5, 0.5],
-                    random_voice=False):
+                    random_voice=False, *, step_hook=None):
         eng = self.estimator.engine()
         ops = eng.ops
         dev = x.device
@@ -187,6 +187,8 @@ class CFM(nn.Module):
                        torch.stack(t_vals))
         for s in range(len(dts)):
             v = eng.step(s, x_op)
+            if step_hook is not None:      # parity tests: the CFG-combined velocity of this step, (B, T, C)
+                step_hook(s, sum(c * v[k * B:(k + 1) * B] for k, c in enumerate(coefs)))
             ops.cfg_euler(xs, v, coefs, dts[s], Tp, st["x_lens"], x_op)
         out = torch.empty(B, C, T, dtype=torch.float32, device=dev)
         ops.btc_to_bct(xs, out)

@@ -175,3 +175,52 @@ def test_sola_oracle_against_reference_golden():
                 assert off == int(z[f"{name}_t{t}_s{s}_off"])
                 assert np.array_equal(out.numpy(), z[f"{name}_t{t}_s{s}_out"])
                 assert np.array_equal(buf.numpy(), z[f"{name}_t{t}_s{s}_buf"])
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size fixtures (oracle/gen_golden_full.py): the oracle at BASELINE frame counts.  Cases are sized so
+# the CPU suite stays within minutes: whole solves where they take seconds, the first Euler step otherwise.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,steps", [("full_small_T323_n25", 25), ("full_tiny_T1291_n10", 10),
+                                        ("full_small_T2580_n25", 1), ("full_base_T2580_n2", 1)])
+def test_oracle_v1_full_size(name, steps, manifest):
+    g = load_golden(name)
+    m = g["meta"]
+    args = configs.v1_model_params(m["model"])
+    sd = synth.synth_state_dict(manifest["keys_" + m["model"]])
+    T, Tp, N = m["T"], m["Tp"], m["n_steps"]
+    mu, prompt, style, z = synth.synth_batch(1, T, Tp, args.DiT.in_channels, args.DiT.content_dim,
+                                             first_id=m["utt_id"])
+    t_span = torch.linspace(0, 1, N + 1)[:steps + 1]
+    out, vs = orc.solve_euler_v1(sd, args, z, torch.tensor([T]), prompt, mu, style, t_span, m["cfg"],
+                                 return_steps=True)
+    fr = torch.from_numpy(g["frames"])
+    for s in range(steps):
+        assert rel_l2(vs[0][s][0][:, fr], g["v_steps"][s]) < 2e-5, (name, s)
+    if steps == N:
+        assert rel_l2(out[0][:, fr], g["out"]) < 2e-5
+
+
+def test_oracle_v2_full_size_first_step(manifest):
+    g = load_golden("full_v2_T2580_n2")
+    m = g["meta"]
+    kw = configs.v2_estimator_kwargs()
+    sd = synth.synth_state_dict(manifest["keys_v2_small"])
+    T, Tp = m["T"], m["Tp"]
+    mu, prompt, style, z = synth.synth_batch(1, T, Tp, kw["in_channels"], kw["content_dim"], first_id=m["utt_id"])
+    t_span = orc.v2_t_span(m["n_steps"])[:2]
+    out = orc.solve_euler_v2(sd, kw, z, torch.tensor([T]), prompt, mu, style, t_span, m["cfg"])
+    fr = torch.from_numpy(g["frames"])
+    x0 = z.clone()
+    x0[..., :Tp] = 0
+    v0 = (out - x0) / float(t_span[1] - t_span[0])
+    assert rel_l2(v0[0][:, fr], g["v_steps"][0]) < 5e-5
+
+
+def test_oracle_bigvgan_full_size_256(manifest):
+    g = load_golden("full_bigvgan22k_256")
+    m = g["meta"]
+    h = configs.bigvgan_h(m["config"])
+    sd = synth.synth_state_dict(manifest["keys_" + m["config"]])
+    wav = orc.bigvgan_forward(sd, h, synth.synth_mel(m["B"], h.num_mels, m["Tm"], seed=m["mel_seed"]))
+    assert rel_l2(wav[:, :, torch.from_numpy(g["idx"])], g["wav"]) < 2e-5
