@@ -31,9 +31,11 @@ extern "C" {
 /* operand element types */
 #define SVC_BF16 0 /* bf16 operands, tcgen05 tensor cores, fp32 accumulate */
 #define SVC_F32 1  /* fp32 operands, fp32 FFMA ("fp32 mode", also small-M GEMMs) */
+#define SVC_F16 2  /* fp16 operands (the reference's default GPU precision: fp16 autocast, inference.py:499),
+                      same tcgen05 kind::f16 path and speed as bf16, 11-bit mantissa */
 
 /* svc_gemm backends */
-#define SVC_BACKEND_AUTO 0 /* bf16 -> tcgen05, fp32 -> SIMT */
+#define SVC_BACKEND_AUTO 0 /* bf16 / fp16 -> tcgen05, fp32 -> SIMT */
 #define SVC_BACKEND_SIMT 1 /* force the SIMT mainloop (debug cross-check) */
 
 /* epilogue activations */
@@ -63,7 +65,7 @@ int svc_version(void);
  *   store out_f32 and/or out_op (operand dtype).
  * ------------------------------------------------------------------------- */
 typedef struct svc_gemm_desc {
-    int dtype;  /* SVC_BF16 / SVC_F32: element type of A, W and out_op */
+    int dtype;  /* SVC_BF16 / SVC_F16 / SVC_F32: element type of A, W and out_op */
     int B, T, N; /* output rows per batch, GEMM columns (before pair reduction) */
     int n_seg;
     const void* a_ptr[SVC_MAX_SEG];

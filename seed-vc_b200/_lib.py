@@ -13,7 +13,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libseedvc_b200.so")
 
-SVC_BF16, SVC_F32 = 0, 1
+SVC_BF16, SVC_F32, SVC_F16 = 0, 1, 2
 BACKEND_AUTO, BACKEND_SIMT = 0, 1
 ACT_NONE, ACT_SILU, ACT_SWIGLU_PAIR, ACT_TANH_SIG_PAIR, ACT_ROPE = 0, 1, 2, 3, 4
 MAX_SEG = 16

@@ -44,7 +44,7 @@ constexpr int AT_THREADS = 128 + AT_QT * 128;   // warpgroup 0: TMA + one MMA is
 
 struct alignas(64) AttnTcParams {
     CUtensorMap qmap, kmap, vmap;  // (H*64, T, B) bf16 views, box {64, 128, 1}
-    __nv_bfloat16* out;
+    uint16_t* out;             // bf16 or fp16 (template parameter F16 of the kernel)
     long long o_bstride, o_rstride;
     const int* kv_len;
     int T, H;
@@ -132,6 +132,9 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 // pipe (8 cycles per warp instruction per SM sub-partition, measured: scripts/ubench/mufu.cu)
 // and by the fixed latencies of a block (barrier round trips, tcgen05.ld/st); three free-running
 // groups per SM keep that pipe ~70% busy, where two groups taking turns reached 60%.
+// F16: operands (Q, K, V, the P tile and the output) are IEEE half instead of bf16 - same instruction, the
+// format bits of the instruction descriptor and the conversions differ.
+template <bool F16>
 __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
     using S = AttnSmem;
     extern __shared__ uint8_t smem_raw[];
@@ -231,8 +234,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
         // cost an elect / 5 x R2UR / branch sequence per MMA (~110 cycles each, measured), which made
         // this thread the pacing resource of the tile's S -> softmax -> PV chain.
         const int g = warp - 1;
-        const uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0);
-        const uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_HD, 0, 1);   // B (=V) MN-major
+        const uint32_t idesc_s = umma_idesc_bf16(AT_BM, AT_BN, 0, 0, F16 ? 0u : 1u);
+        const uint32_t idesc_o = umma_idesc_bf16(AT_BM, AT_HD, 0, 1, F16 ? 0u : 1u);   // B (=V) MN-major
         // descriptor lo words of the smem regions (address field only varies)
         const uint32_t qlo = desc_lo(smem_u32(smem + S::Q_OFF)) + g * (S::QTILE >> 4);
         const uint32_t k_lo0 = desc_lo(smem_u32(smem + S::K_OFF));
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                         const float2 pp = make_float2(fast_exp2(x.x), fast_exp2(x.y));
 #endif
                         la2[(i >> 1) & 3] = __fadd2_rn(la2[(i >> 1) & 3], pp);
-                        pk[c * 16 + (i >> 1)] = pack_bf16(pp.x, pp.y);
+                        pk[c * 16 + (i >> 1)] = pack_op16<F16>(pp.x, pp.y);
                     }
                 const float2 l2 = __fadd2_rn(__fadd2_rn(la2[0], la2[1]), __fadd2_rn(la2[2], la2[3]));
                 return l2.x + l2.y;
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
             tc_fence_after();
             const int t = q0 + g * AT_BM + row;
             const float inv_l = 1.0f / l_run;
-            __nv_bfloat16* o = p.out + static_cast<long long>(b) * p.o_bstride +
+            uint16_t* o = p.out + static_cast<long long>(b) * p.o_bstride +
                                static_cast<long long>(t) * p.o_rstride + h * AT_HD;
 #pragma unroll
             for (int c = 0; c < AT_HD; c += 32) {
@@ -428,10 +431,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
                     for (int d = 0; d < 32; d += 8) {
                         uint4 q;
-                        q.x = pack_bf16(__uint_as_float(r[d]) * inv_l, __uint_as_float(r[d + 1]) * inv_l);
-                        q.y = pack_bf16(__uint_as_float(r[d + 2]) * inv_l, __uint_as_float(r[d + 3]) * inv_l);
-                        q.z = pack_bf16(__uint_as_float(r[d + 4]) * inv_l, __uint_as_float(r[d + 5]) * inv_l);
-                        q.w = pack_bf16(__uint_as_float(r[d + 6]) * inv_l, __uint_as_float(r[d + 7]) * inv_l);
+                        q.x = pack_op16<F16>(__uint_as_float(r[d]) * inv_l, __uint_as_float(r[d + 1]) * inv_l);
+                        q.y = pack_op16<F16>(__uint_as_float(r[d + 2]) * inv_l, __uint_as_float(r[d + 3]) * inv_l);
+                        q.z = pack_op16<F16>(__uint_as_float(r[d + 4]) * inv_l, __uint_as_float(r[d + 5]) * inv_l);
+                        q.w = pack_op16<F16>(__uint_as_float(r[d + 6]) * inv_l, __uint_as_float(r[d + 7]) * inv_l);
                         *reinterpret_cast<uint4*>(o + c + d) = q;
                     }
                 }
@@ -523,7 +526,7 @@ extern "C" int svc_attention(const void* q, const void* k, const void* v, long l
         return SVC_ERR_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (dtype == SVC_BF16 && backend == SVC_BACKEND_AUTO) {
+    if ((dtype == SVC_BF16 || dtype == SVC_F16) && backend == SVC_BACKEND_AUTO) {
         AttnTcParams p;
         if (!encode_bf16_map(&p.qmap, q, H * AT_HD, T, qkv_rstride, B, qkv_bstride, AT_BM) ||
             !encode_bf16_map(&p.kmap, k, H * AT_HD, T, qkv_rstride, B, qkv_bstride, AT_BN) ||
@@ -535,7 +538,7 @@ extern "C" int svc_attention(const void* q, const void* k, const void* v, long l
             svc_set_error("svc_attention: out must be 16-byte aligned");
             return SVC_ERR_ARG;
         }
-        p.out = static_cast<__nv_bfloat16*>(out);
+        p.out = static_cast<uint16_t*>(out);
         p.o_bstride = out_bstride;
         p.o_rstride = out_rstride;
         p.kv_len = kv_len;
@@ -543,7 +546,9 @@ extern "C" int svc_attention(const void* q, const void* k, const void* v, long l
         p.H = H;
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 AttnSmem::TOTAL);
+            cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  AttnSmem::TOTAL);
             attr_set = true;
         }
@@ -556,7 +561,8 @@ extern "C" int svc_attention(const void* q, const void* k, const void* v, long l
         }
         p.total_items = static_cast<int>(total);
         const int grid = p.total_items < 148 ? p.total_items : 148;     // one persistent CTA per SM
-        attention_tc_kernel<<<grid, AT_THREADS, AttnSmem::TOTAL, st>>>(p);
+        if (dtype == SVC_F16) attention_tc_kernel<true><<<grid, AT_THREADS, AttnSmem::TOTAL, st>>>(p);
+        else attention_tc_kernel<false><<<grid, AT_THREADS, AttnSmem::TOTAL, st>>>(p);
         SVC_CHECK_LAUNCH();
         return SVC_OK;
     }
@@ -565,6 +571,10 @@ extern "C" int svc_attention(const void* q, const void* k, const void* v, long l
         attention_simt_kernel<float><<<grid, 128, 0, st>>>(
             static_cast<const float*>(q), static_cast<const float*>(k), static_cast<const float*>(v),
             qkv_bstride, qkv_rstride, static_cast<float*>(out), out_bstride, out_rstride, T, kv_len);
+    else if (dtype == SVC_F16)
+        attention_simt_kernel<__half><<<grid, 128, 0, st>>>(
+            static_cast<const __half*>(q), static_cast<const __half*>(k), static_cast<const __half*>(v),
+            qkv_bstride, qkv_rstride, static_cast<__half*>(out), out_bstride, out_rstride, T, kv_len);
     else
         attention_simt_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(
             static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k),

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -254,9 +255,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format f32 (1) at [4,6),
 // a/b format bf16 (1) at [7,10)/[10,13), a_major [15], b_major [16], N>>3 at [17,23),
 // M>>4 at [24,29).
+// ab_fmt: 1 = bf16 (default), 0 = fp16 - both operands of kind::f16 share the format here.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major,
-                                                       int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+                                                       int b_mn_major, uint32_t ab_fmt = 1u) {
+    return (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
            (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
            (static_cast<uint32_t>(M >> 4) << 24);
 }
@@ -280,6 +282,42 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// two floats -> one 32-bit word of the 16-bit operand format (F16: IEEE half, else bf16)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_op16(float lo, float hi) {
+    if constexpr (F16) return pack_f16(lo, hi);
+    else return pack_bf16(lo, hi);
+}
+
+// two floats -> one packed word of 16-bit type TO (bf16 or half)
+template <typename TO>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+    return pack_bf16(lo, hi);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+    return pack_f16(lo, hi);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<float>(float lo, float) {   // never used: keeps `if constexpr` branches well-formed
+    return __float_as_uint(lo);
+}
+
+// run-time format variants (SIMT / fallback paths, where the branch cost does not matter)
+__device__ __forceinline__ uint32_t pack_op16_rt(float lo, float hi, int f16) {
+    return f16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+}
+__device__ __forceinline__ uint16_t cvt_op16_rt(float v, int f16) {
+    if (f16) return __half_as_ushort(__float2half_rn(v));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
 template <>
@@ -290,8 +328,16 @@ template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) {
     return __bfloat162float(v);
 }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) {
+    return __half2float(v);
+}
 template <typename T>
 __device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) {
+    return __float2half_rn(v);
+}
 template <>
 __device__ __forceinline__ float from_f32<float>(float v) {
     return v;

@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(256) norm_mod_kernel(
                 *reinterpret_cast<float4*>(orow + c) = make_float4(y[0], y[1], y[2], y[3]);
             } else {
                 uint2 q;
-                q.x = pack_bf16(y[0], y[1]);
-                q.y = pack_bf16(y[2], y[3]);
+                q.x = pack2<TO>(y[0], y[1]);
+                q.y = pack2<TO>(y[2], y[3]);
                 *reinterpret_cast<uint2*>(orow + c) = q;
             }
             if (raw != nullptr) {      // un-normalised copy of the row in the operand dtype (same layout as out)
@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(256) norm_mod_kernel(
                     *reinterpret_cast<float4*>(rrow + c) = v[i];
                 } else {
                     uint2 q;
-                    q.x = pack_bf16(v[i].x, v[i].y);
-                    q.y = pack_bf16(v[i].z, v[i].w);
+                    q.x = pack2<TO>(v[i].x, v[i].y);
+                    q.y = pack2<TO>(v[i].z, v[i].w);
                     *reinterpret_cast<uint2*>(rrow + c) = q;
                 }
             }
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(
                 *reinterpret_cast<float4*>(x_op + e) = xv;
             } else {
                 uint2 q;
-                q.x = pack_bf16(xv.x, xv.y);
-                q.y = pack_bf16(xv.z, xv.w);
+                q.x = pack2<TO>(xv.x, xv.y);
+                q.y = pack2<TO>(xv.z, xv.w);
                 *reinterpret_cast<uint2*>(x_op + e) = q;
             }
         }
@@ -257,6 +257,10 @@ static int norm_mod_impl(const float* x, long long x_bstride, long long x_rstrid
         return SVC_ERR_ARG;
     }
     const int esz = out_dtype == SVC_F32 ? 4 : 2;
+    if (out_dtype != SVC_F32 && out_dtype != SVC_BF16 && out_dtype != SVC_F16) {
+        svc_set_error("svc_norm_mod: bad out_dtype");
+        return SVC_ERR_ARG;
+    }
     if (!aligned16(x) || (x_bstride % 4) || (x_rstride % 4) || !aligned16(out) ||
         (o_bstride * esz) % 8 || (o_rstride * esz) % 8 || (gamma && !aligned16(gamma)) ||
         (mul && !aligned16(mul)) || (add && !aligned16(add))) {
@@ -275,6 +279,10 @@ static int norm_mod_impl(const float* x, long long x_bstride, long long x_rstrid
         if (D <= 512) LAUNCH_NORM(float, 4);
         else if (D <= 1024) LAUNCH_NORM(float, 8);
         else LAUNCH_NORM(float, 16);
+    } else if (out_dtype == SVC_F16) {
+        if (D <= 512) LAUNCH_NORM(__half, 4);
+        else if (D <= 1024) LAUNCH_NORM(__half, 8);
+        else LAUNCH_NORM(__half, 16);
     } else {
         if (D <= 512) LAUNCH_NORM(__nv_bfloat16, 4);
         else if (D <= 1024) LAUNCH_NORM(__nv_bfloat16, 8);
@@ -316,6 +324,9 @@ extern "C" int svc_cfg_euler(float* x, const float* v, int n_branch, float c0, f
         cfg_euler_kernel<float><<<blocks, 256, 0, st>>>(x, v, n_branch, c0, c1, c2, dt, B, T, C,
                                                         prompt_len, x_lens, static_cast<float*>(x_op),
                                                         x_op != nullptr);
+    else if (op_dtype == SVC_F16)
+        cfg_euler_kernel<__half><<<blocks, 256, 0, st>>>(x, v, n_branch, c0, c1, c2, dt, B, T, C, prompt_len,
+                                                         x_lens, static_cast<__half*>(x_op), x_op != nullptr);
     else
         cfg_euler_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
             x, v, n_branch, c0, c1, c2, dt, B, T, C, prompt_len, x_lens,
@@ -332,6 +343,9 @@ extern "C" int svc_bct_to_btc(const float* in, void* out, long long o_bstride, l
     if (out_dtype == SVC_F32)
         bct_to_btc_kernel<float><<<grid, 256, 0, st>>>(in, static_cast<float*>(out), o_bstride,
                                                        o_rstride, C, T, zero_from, zero_to);
+    else if (out_dtype == SVC_F16)
+        bct_to_btc_kernel<__half><<<grid, 256, 0, st>>>(in, static_cast<__half*>(out), o_bstride, o_rstride, C, T,
+                                                        zero_from, zero_to);
     else
         bct_to_btc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
             in, static_cast<__nv_bfloat16*>(out), o_bstride, o_rstride, C, T, zero_from, zero_to);
@@ -352,6 +366,8 @@ extern "C" int svc_cast(const float* in, void* out, long long n, int out_dtype, 
     const unsigned blocks = static_cast<unsigned>(std::min<long long>((n + 255) / 256, kNumSMs * 16));
     if (out_dtype == SVC_F32)
         cast_kernel<float><<<blocks, 256, 0, st>>>(in, static_cast<float*>(out), n);
+    else if (out_dtype == SVC_F16)
+        cast_kernel<__half><<<blocks, 256, 0, st>>>(in, static_cast<__half*>(out), n);
     else
         cast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(in, static_cast<__nv_bfloat16*>(out), n);
     SVC_CHECK_LAUNCH();
@@ -369,7 +385,7 @@ extern "C" int svc_reflect_halo(void* buf, long long bstride, long long rstride,
     if (dtype == SVC_F32)
         reflect_halo_kernel<float><<<grid, 128, 0, st>>>(static_cast<float*>(buf), bstride, rstride, T,
                                                          C, pad, lens);
-    else
+    else      // a row copy: the 16-bit instantiation serves bf16 and fp16 alike
         reflect_halo_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(static_cast<__nv_bfloat16*>(buf),
                                                                  bstride, rstride, T, C, pad, lens);
     SVC_CHECK_LAUNCH();
@@ -494,6 +510,10 @@ extern "C" int svc_interp_rows(const float* src, long long src_bstride, long lon
         interp_rows_kernel<float><<<grid, 128, 0, st>>>(src, src_bstride, src_rstride, idx, add_vec, emb,
                                                         emb_q, q_bstride, emb_idx, static_cast<float*>(out),
                                                         out_bstride, out_rstride, D);
+    else if (dtype == SVC_F16)
+        interp_rows_kernel<__half><<<grid, 128, 0, st>>>(src, src_bstride, src_rstride, idx, add_vec, emb, emb_q,
+                                                         q_bstride, emb_idx, static_cast<__half*>(out), out_bstride,
+                                                         out_rstride, D);
     else
         interp_rows_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(
             src, src_bstride, src_rstride, idx, add_vec, emb, emb_q, q_bstride, emb_idx,
@@ -526,6 +546,15 @@ extern "C" int svc_groupnorm1_mish(const float* x, long long bstride, long long 
             gn1_mish_kernel<float, false><<<grid, 256, 0, st>>>(x, bstride, rstride, gamma, beta, eps, stats_ws,
                                                                static_cast<float*>(out), out_bstride,
                                                                out_rstride, T, C);
+    } else if (dtype == SVC_F16) {
+        if (precise)
+            gn1_mish_kernel<__half, true><<<grid, 256, 0, st>>>(x, bstride, rstride, gamma, beta, eps, stats_ws,
+                                                               static_cast<__half*>(out), out_bstride, out_rstride,
+                                                               T, C);
+        else
+            gn1_mish_kernel<__half, false><<<grid, 256, 0, st>>>(x, bstride, rstride, gamma, beta, eps, stats_ws,
+                                                                static_cast<__half*>(out), out_bstride, out_rstride,
+                                                                T, C);
     } else {
         if (precise)
             gn1_mish_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(

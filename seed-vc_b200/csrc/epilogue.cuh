@@ -28,6 +28,7 @@ struct EpiParams {
     void* out_op;
     long long oo_bstride, oo_rstride;
     int op_is_f32;
+    int op_is_f16;             // 16-bit operand format: 1 = IEEE half, 0 = bf16
     int vec_ok;  // every pointer / stride involved is 16-byte aligned
 };
 
@@ -62,6 +63,7 @@ inline EpiParams make_epi_params(const svc_gemm_desc& d) {
     e.oo_bstride = d.oo_bstride;
     e.oo_rstride = d.oo_rstride;
     e.op_is_f32 = d.dtype == SVC_F32;
+    e.op_is_f16 = d.dtype == SVC_F16;
     auto al = [](const void* p, long long s0, long long s1, int esz) {
         return p == nullptr || ((reinterpret_cast<uintptr_t>(p) % 16 == 0) &&
                                 ((s0 * esz) % 16 == 0) && ((s1 * esz) % 16 == 0));
@@ -192,24 +194,25 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, int b, int t,
                     if (j < co && c0 + j < e.N_out) o[j] = v[j];
             }
         } else {
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(e.out_op) +
-                               static_cast<long long>(b) * e.oo_bstride +
-                               static_cast<long long>(t) * e.oo_rstride + c0;
+            uint16_t* o = static_cast<uint16_t*>(e.out_op) +
+                          static_cast<long long>(b) * e.oo_bstride +
+                          static_cast<long long>(t) * e.oo_rstride + c0;
+            const int f16 = e.op_is_f16;
             if (vec && (co % 8 == 0) && (c0 % 8 == 0)) {
 #pragma unroll
                 for (int j = 0; j < CO_MAX; j += 8)
                     if (j < co) {
                         uint4 q;
-                        q.x = pack_bf16(v[j], v[j + 1]);
-                        q.y = pack_bf16(v[j + 2], v[j + 3]);
-                        q.z = pack_bf16(v[j + 4], v[j + 5]);
-                        q.w = pack_bf16(v[j + 6], v[j + 7]);
+                        q.x = pack_op16_rt(v[j], v[j + 1], f16);
+                        q.y = pack_op16_rt(v[j + 2], v[j + 3], f16);
+                        q.z = pack_op16_rt(v[j + 4], v[j + 5], f16);
+                        q.w = pack_op16_rt(v[j + 6], v[j + 7], f16);
                         *reinterpret_cast<uint4*>(o + j) = q;
                     }
             } else {
 #pragma unroll
                 for (int j = 0; j < CO_MAX; ++j)
-                    if (j < co && c0 + j < e.N_out) o[j] = __float2bfloat16_rn(v[j]);
+                    if (j < co && c0 + j < e.N_out) o[j] = cvt_op16_rt(v[j], f16);
             }
         }
     }

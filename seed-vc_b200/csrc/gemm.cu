@@ -284,9 +284,9 @@ transpose:
                         *reinterpret_cast<float4*>(static_cast<float*>(e.out_op) + off) = x;
                     } else {
                         uint2 pk;
-                        pk.x = pack_bf16(x.x, x.y);
-                        pk.y = pack_bf16(x.z, x.w);
-                        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(e.out_op) + off) = pk;
+                        pk.x = pack_op16_rt(x.x, x.y, e.op_is_f16);
+                        pk.y = pack_op16_rt(x.z, x.w, e.op_is_f16);
+                        *reinterpret_cast<uint2*>(static_cast<uint16_t*>(e.out_op) + off) = pk;
                     }
                 }
             }
@@ -316,7 +316,7 @@ transpose:
                     const long long off = static_cast<long long>(b) * e.oo_bstride +
                                           static_cast<long long>(t) * e.oo_rstride + cc;
                     if (e.op_is_f32) static_cast<float*>(e.out_op)[off] = x;
-                    else static_cast<__nv_bfloat16*>(e.out_op)[off] = __float2bfloat16_rn(x);
+                    else static_cast<uint16_t*>(e.out_op)[off] = cvt_op16_rt(x, e.op_is_f16);
                 }
             }
         }
@@ -428,12 +428,13 @@ __device__ __forceinline__ void epilogue_item_tma(const TcParams& p, float* stag
     __syncwarp();          // everyone has read the fp32 tile; overwrite it with the final tile
     if (p.store_mode == 1) {
         uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
+        const int f16 = e.op_is_f16;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rsub;
             uint2 pk;
-            pk.x = pack_bf16(a[it].x, a[it].y);
-            pk.y = pack_bf16(a[it].z, a[it].w);
+            pk.x = pack_op16_rt(a[it].x, a[it].y, f16);
+            pk.y = pack_op16_rt(a[it].z, a[it].w, f16);
             *reinterpret_cast<uint2*>(sb + r * 64 + q * 8) = pk;
         }
     } else {
@@ -558,11 +559,19 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     if (p.store_mode == 1 || p.dual) {
         uint8_t* row = sb + (p.dual ? 4096 : 0) + lane * 64;
         const int sw = (lane >> 1) & 3;
+        if (e.op_is_f16) {         // warp-uniform: one conversion flavour per launch
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(row + ((q ^ sw) << 4)) =
-                make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
-                           pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(row + ((q ^ sw) << 4)) =
+                    make_uint4(pack_f16(v[8 * q], v[8 * q + 1]), pack_f16(v[8 * q + 2], v[8 * q + 3]),
+                               pack_f16(v[8 * q + 4], v[8 * q + 5]), pack_f16(v[8 * q + 6], v[8 * q + 7]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(row + ((q ^ sw) << 4)) =
+                    make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                               pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+        }
     }
     if (p.store_mode != 1) {
         uint8_t* row = sb + lane * 128;
@@ -671,7 +680,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 const int n0 = (tile % p.n_tiles) * BN;
                 int n_umma = p.epi.N - n0;
                 n_umma = n_umma > BN ? BN : ((n_umma + 15) & ~15);
-                const uint32_t idesc = umma_idesc_bf16(BM, n_umma, 0, 0);
+                const uint32_t idesc = umma_idesc_bf16(BM, n_umma, 0, 0, p.epi.op_is_f16 ? 0u : 1u);
                 const int acc = it & 1;
                 GTRACE(1, it, 0);
                 mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);   // epilogue drained this buffer
@@ -1194,6 +1203,8 @@ static int gemm_simt(const svc_gemm_desc& d, cudaStream_t stream) {
     const long long blocks = static_cast<long long>(d.B) * p.tiles_per_batch * p.n_tiles;
     if (d.dtype == SVC_F32)
         gemm_simt_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+    else if (d.dtype == SVC_F16)
+        gemm_simt_kernel<__half><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
     else
         gemm_simt_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
     SVC_CHECK_LAUNCH();
@@ -1207,8 +1218,8 @@ extern "C" int svc_gemm(const svc_gemm_desc* d, int backend, void* stream) {
         svc_set_error("svc_gemm: bad descriptor");
         return SVC_ERR_ARG;
     }
-    if (d->dtype != SVC_BF16 && d->dtype != SVC_F32) {
-        svc_set_error("svc_gemm: dtype must be SVC_BF16 or SVC_F32");
+    if (d->dtype != SVC_BF16 && d->dtype != SVC_F32 && d->dtype != SVC_F16) {
+        svc_set_error("svc_gemm: dtype must be SVC_BF16, SVC_F16 or SVC_F32");
         return SVC_ERR_ARG;
     }
     if ((d->act == SVC_ACT_SWIGLU_PAIR || d->act == SVC_ACT_TANH_SIG_PAIR) && (d->N % 2)) {
@@ -1220,7 +1231,7 @@ extern "C" int svc_gemm(const svc_gemm_desc* d, int backend, void* stream) {
         return SVC_ERR_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (d->dtype == SVC_BF16 && backend == SVC_BACKEND_AUTO) return svc::gemm_tc(*d, st);
+    if (d->dtype != SVC_F32 && backend == SVC_BACKEND_AUTO) return svc::gemm_tc(*d, st);
     return svc::gemm_simt(*d, st);
 }
 

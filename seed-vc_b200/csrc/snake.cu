@@ -153,6 +153,14 @@ __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
     return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
 }
 
+template <>
+__device__ __forceinline__ float4 load4<__half>(const __half* p) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 template <typename TI, typename TO, int CT, int LPT, bool PRECISE>
 __global__ void __launch_bounds__(256) snake_aa2_kernel(const TI* __restrict__ x, TO* __restrict__ out,
                                                         const float* __restrict__ a_p,
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(256) snake_aa2_kernel(const TI* __restrict__ x
         if constexpr (sizeof(TO) == 4) {
             *reinterpret_cast<float2*>(ob + static_cast<long long>(n) * C) = y;
         } else {
-            *reinterpret_cast<__nv_bfloat162*>(ob + static_cast<long long>(n) * C) = __floats2bfloat162_rn(y.x, y.y);
+            *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(n) * C) = pack2<TO>(y.x, y.y);
         }
     };
     const int n_last = min(n0 + LPT, L) - 1;
@@ -400,6 +408,9 @@ extern "C" int svc_snake_aa(const void* x, int x_dtype, void* out, int out_dtype
     if (x_dtype == SVC_F32 && out_dtype == SVC_BF16) { SNAKE_DISPATCH(float, __nv_bfloat16); }
     if (x_dtype == SVC_BF16 && out_dtype == SVC_BF16) { SNAKE_DISPATCH(__nv_bfloat16, __nv_bfloat16); }
     if (x_dtype == SVC_BF16 && out_dtype == SVC_F32) { SNAKE_DISPATCH(__nv_bfloat16, float); }
+    if (x_dtype == SVC_F32 && out_dtype == SVC_F16) { SNAKE_DISPATCH(float, __half); }
+    if (x_dtype == SVC_F16 && out_dtype == SVC_F16) { SNAKE_DISPATCH(__half, __half); }
+    if (x_dtype == SVC_F16 && out_dtype == SVC_F32) { SNAKE_DISPATCH(__half, float); }
 #undef SNAKE_DISPATCH
     svc_set_error("svc_snake_aa: unsupported dtype");
     return SVC_ERR_UNSUPPORTED;

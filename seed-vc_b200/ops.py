@@ -4,8 +4,10 @@ PyTorch is used only for device memory and the current stream; every method
 hands raw pointers, sizes and strides to ``libseedvc_b200.so``.  ``Ops`` refuses
 non-CUDA tensors: there is no CPU path.
 
-``mode``: ``"bf16"`` (bf16 operands on tcgen05 tensor cores, fp32 accumulate,
-fp32 residual streams) or ``"fp32"`` (fp32 operands, FFMA kernels).
+``mode``: ``"fp16"`` (IEEE-half operands on tcgen05 tensor cores, fp32 accumulate, fp32
+residual streams - the reference's own default GPU precision, fp16 autocast, inference.py:499),
+``"bf16"`` (same kernels with bf16 operands: 8 instead of 11 mantissa bits, wider range) or
+``"fp32"`` (fp32 operands, FFMA kernels).
 """
 from __future__ import annotations
 
@@ -14,8 +16,10 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_ROPE, BACKEND_AUTO, BACKEND_SIMT, SVC_BF16, SVC_F32, GemmDesc,
+from ._lib import (ACT_NONE, ACT_ROPE, BACKEND_AUTO, BACKEND_SIMT, SVC_BF16, SVC_F16, SVC_F32, GemmDesc,
                    check)
+
+MODES = {"bf16": (torch.bfloat16, SVC_BF16), "fp16": (torch.float16, SVC_F16), "fp32": (torch.float32, SVC_F32)}
 
 
 def _ptr(t):
@@ -24,12 +28,11 @@ def _ptr(t):
 
 class Ops:
     def __init__(self, mode: str = "bf16", force_simt: bool = False):
-        if mode not in ("bf16", "fp32"):
-            raise ValueError("mode must be 'bf16' or 'fp32'")
+        if mode not in MODES:
+            raise ValueError("mode must be 'fp16', 'bf16' or 'fp32'")
         self.lib = _lib.load_library()
         self.mode = mode
-        self.op_dtype = torch.bfloat16 if mode == "bf16" else torch.float32
-        self.op_code = SVC_BF16 if mode == "bf16" else SVC_F32
+        self.op_dtype, self.op_code = MODES[mode]
         self.backend = BACKEND_SIMT if force_simt else BACKEND_AUTO
         self.precise = 1 if mode == "fp32" else 0
         self.launches = 0
@@ -80,6 +83,8 @@ class Ops:
     def _code(self, dt):
         if dt == torch.bfloat16:
             return SVC_BF16
+        if dt == torch.float16:
+            return SVC_F16
         if dt == torch.float32:
             return SVC_F32
         raise TypeError(f"unsupported dtype {dt}")

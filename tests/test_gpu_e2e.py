@@ -20,7 +20,7 @@ from seedvc_b200.flow_matching_v2 import CFM as CFMv2, DiT as DiTv2  # noqa: E40
 from conftest import load_golden, rel_l2  # noqa: E402
 
 DEV = "cuda"
-TOL = {"fp32": 1e-3, "bf16": 1e-2}
+TOL = {"fp32": 1e-3, "bf16": 1e-2, "fp16": 3e-3}
 V1 = ["v1_small_scaled_cfg", "v1_small_scaled_nocfg", "v1_tiny_scaled_cfg", "v1_base_scaled_cfg",
       "v1_tiny_full", "v1_small_full", "v1_base_full"]
 V2 = ["v2_small_3branch", "v2_small_spk_only", "v2_small_txt_only", "v2_small_nocfg",
@@ -43,7 +43,7 @@ def v1_model(model, scaled, mode):
     return cfm, args
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", V1)
 def test_v1_golden(name, mode):
     g = load_golden(name)
@@ -66,7 +66,7 @@ def test_v1_golden(name, mode):
     assert e_v < TOL[mode] and e_o < TOL[mode]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", V2)
 def test_v2_golden(name, mode):
     g = load_golden(name)
@@ -87,7 +87,7 @@ def test_v2_golden(name, mode):
     assert e < TOL[mode]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", ["bigvgan_22k_t12", "bigvgan_22k_b2_t7", "bigvgan_44k_t6"])
 def test_bigvgan_golden(name, mode):
     g = load_golden(name)
@@ -105,7 +105,7 @@ def test_bigvgan_golden(name, mode):
     assert e < TOL[mode]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
 def test_v1_against_oracle_ragged_batch(mode, manifest):
     """Seeded batch of 3 utterances of different lengths vs the oracle's per-utterance runs."""
     import seedvc_oracle as orc
@@ -213,7 +213,7 @@ def test_long_form_chunks_match_sequential_loop():
     assert e < 1e-3
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
 def test_length_regulator_golden(mode):
     """InterpolateRegulator on the CUDA kernels vs the REAL reference module's outputs."""
     import json

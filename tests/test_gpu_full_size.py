@@ -17,7 +17,7 @@ from seedvc_b200.flow_matching_v2 import CFM as CFMv2, DiT as DiTv2  # noqa: E40
 from conftest import load_golden, rel_l2  # noqa: E402
 
 DEV = "cuda"
-TOL = {"fp32": 1e-3, "bf16": 1e-2}
+TOL = {"fp32": 1e-3, "bf16": 1e-2, "fp16": 3e-3}
 SAMPLER = ["full_small_T2580_n25", "full_small_T323_n25", "full_tiny_T1291_n10", "full_base_T2580_n2",
            "full_v2_T2580_n2"]
 VOCODER = ["full_bigvgan22k_256", "full_bigvgan22k_2150", "full_bigvgan44k_256"]
@@ -42,7 +42,7 @@ def sampler_model(kind, model, mode):
     return cfm, dims
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", SAMPLER)
 def test_full_size_sampler_per_step_and_end_to_end(name, mode):
     g = load_golden(name)
@@ -75,7 +75,7 @@ def test_full_size_sampler_per_step_and_end_to_end(name, mode):
     assert e_out < TOL[mode]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", VOCODER)
 def test_full_size_vocoder(name, mode):
     g = load_golden(name)

@@ -90,7 +90,7 @@ def run_gemm_case(mode, simt, B, T, N, Ks, shifts=None, rows=None, bias=False, r
         assert e < tol, f"out_f32 rel-L2 {e}"
     if out_op is not None:
         e2 = rel_l2(out_op.float(), out_ref)
-        assert e2 < (1e-5 if mode == "fp32" else 4e-3), f"out_op rel-L2 {e2}"
+        assert e2 < {"fp32": 1e-5, "bf16": 4e-3, "fp16": 6e-4}[mode], f"out_op rel-L2 {e2}"
 
 
 GEMM_SHAPES = [
@@ -110,13 +110,13 @@ GEMM_SHAPES = [
 
 
 @pytest.mark.parametrize("shape", GEMM_SHAPES)
-@pytest.mark.parametrize("mode,simt", [("bf16", False), ("bf16", True), ("fp32", False)])
+@pytest.mark.parametrize("mode,simt", [("bf16", False), ("bf16", True), ("fp16", False), ("fp16", True), ("fp32", False)])
 def test_gemm_plain(shape, mode, simt):
     B, T, N, Ks = shape
     run_gemm_case(mode, simt, B, T, N, Ks)
 
 
-@pytest.mark.parametrize("mode,simt", [("bf16", False), ("fp32", False)])
+@pytest.mark.parametrize("mode,simt", [("bf16", False), ("fp16", False), ("fp32", False)])
 def test_gemm_epilogues(mode, simt):
     run_gemm_case(mode, simt, 2, 150, 256, [128], bias=True, rowbias=True, res=True, alpha=0.5,
                   both_out=True)
@@ -129,7 +129,7 @@ def test_gemm_epilogues(mode, simt):
     run_gemm_case(mode, simt, 2, 150, 384, [128], rope=True, both_out=True)
 
 
-@pytest.mark.parametrize("mode,simt", [("bf16", False), ("fp32", False)])
+@pytest.mark.parametrize("mode,simt", [("bf16", False), ("fp16", False), ("fp32", False)])
 def test_gemm_store_paths(mode, simt):
     """Every output pattern the tensor-core path specialises: operand-only tile stores (plain, SiLU,
     SwiGLU / gate pairs, RoPE with and without the pair-major table), fp32-only stores (plain, in-place
@@ -152,7 +152,7 @@ def test_gemm_store_paths(mode, simt):
     run_gemm_case(mode, simt, 2, 333, 1536, [512], rope=True, out_kind="op")
 
 
-@pytest.mark.parametrize("mode,simt", [("bf16", False), ("fp32", False)])
+@pytest.mark.parametrize("mode,simt", [("bf16", False), ("fp16", False), ("fp32", False)])
 def test_gemm_segments(mode, simt):
     # concat-free linear over two operands
     run_gemm_case(mode, simt, 2, 140, 128, [128, 128], bias=True)
@@ -166,7 +166,7 @@ def test_gemm_segments(mode, simt):
     # taps over a padded buffer (WaveNet reflect layout): rows = T + 4
     run_gemm_case(mode, simt, 2, 131, 256, [128] * 5, shifts=[0, 1, 2, 3, 4], rows=135, rowbias=True,
                   act=3, share_a=True)
-    if mode == "bf16":   # more than 4 distinct operand views is refused, not mis-computed
+    if mode != "fp32":   # more than 4 distinct operand views is refused, not mis-computed
         with pytest.raises(_lib.SvcError):
             run_gemm_case(mode, simt, 1, 64, 32, [32] * 5)
 
@@ -184,7 +184,7 @@ def test_gemm_conv_taps_share_weight_buffer():
     assert rel_l2(out, ref) < 2e-4
 
 
-@pytest.mark.parametrize("mode,simt", [("bf16", False), ("bf16", True), ("fp32", False)])
+@pytest.mark.parametrize("mode,simt", [("bf16", False), ("bf16", True), ("fp16", False), ("fp16", True), ("fp32", False)])
 @pytest.mark.parametrize("B,T,H,lens", [(1, 65, 2, None), (2, 128, 2, [128, 100]),
                                         (2, 323, 6, [323, 17]), (1, 1291, 8, None),
                                         (3, 257, 2, [257, 256, 129])])
@@ -205,7 +205,7 @@ def test_attention(mode, simt, B, T, H, lens):
 
 
 @pytest.mark.parametrize("D", [128, 384, 512, 768])
-@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "fp32"])
 def test_norm_mod(D, mode):
     ops, emu = ops_for(mode), EmuOps()
     B, T = 2, 77
@@ -228,7 +228,7 @@ def test_norm_mod(D, mode):
 
 @pytest.mark.parametrize("C,L", [(24, 1000), (48, 515), (96, 300), (768, 70), (192, 129), (16, 40),
                                  (32, 12), (8, 5)])
-@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "fp32"])
 def test_snake(C, L, mode):
     ops, emu = ops_for(mode), EmuOps()
     B = 2
@@ -241,8 +241,8 @@ def test_snake(C, L, mode):
     emu.snake(x, ref, a, inv_b)
     e = rel_l2(out.float(), ref)
     assert e < (1e-5 if mode == "fp32" else 4e-3), f"rel-L2 {e}"
-    if mode == "bf16":   # bf16 input variant
-        xb = x.to(torch.bfloat16)
+    if mode != "fp32":   # 16-bit input variant
+        xb = x.to(ops.op_dtype)
         ops.snake(xb, out, a, inv_b)
         emu.snake(xb.float(), ref, a, inv_b)
         assert rel_l2(out.float(), ref) < 4e-3
@@ -276,19 +276,21 @@ def test_snake_conv_post(use_tanh):
     assert float(out.abs().max()) <= 1.0
 
 
-def test_cfg_euler_and_layout():
-    ops, emu = ops_for("bf16"), EmuOps()
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_cfg_euler_and_layout(mode):
+    ops, emu = ops_for(mode), EmuOps()
+    od16 = ops.op_dtype
     B, T, C = 3, 101, 80
     lens = torch.tensor([101, 64, 7], dtype=torch.int32, device=DEV)
     for nb, coefs in ((1, [1.0]), (2, [1.7, -0.7]), (3, [2.4, -0.7, -0.7])):
         x = rnd(B, T, C, seed=nb)
         v = rnd(nb * B, T, C, seed=nb + 5)
         xr = x.clone()
-        x_op = torch.zeros(B, T, C, dtype=torch.bfloat16, device=DEV)
+        x_op = torch.zeros(B, T, C, dtype=od16, device=DEV)
         ops.cfg_euler(x, v, coefs, 0.04, 9, lens, x_op)
         emu.cfg_euler(xr, v, coefs, 0.04, 9, lens, None)
         assert rel_l2(x, xr) < 1e-6
-        assert torch.equal(x_op, x.to(torch.bfloat16))
+        assert torch.equal(x_op, x.to(od16))
     src = rnd(2, 80, 45, seed=3)
     out = torch.zeros(2, 45, 80, device=DEV)
     ops.bct_to_btc(src, out, zero_from=0, zero_to=5)
