@@ -53,7 +53,7 @@ WORKLOADS = {
     "profile": dict(kind="v1", model="whisper_small", voc="bigvgan_22k", B=8, T=2580, Tp=430, steps=2, cfg=0.7,
                     scaling="weak"),          # config-2 shapes, short (ncu)
 }
-VOC_CHUNK = 32            # utterances per vocoder call (bounds the stage buffers: ~10 GB at 32 x 2150 frames)
+VOC_FRAMES = 32 * 2150    # mel frames per vocoder call (bounds the stage buffers: ~10 GB at 32 x 2150 frames)
 # streaming geometry of config 5 (real-time-gui.py:859-928 with block 0.18 s, crossfade 0.04 s, extra_ce 2.5 s,
 # extra_right 0.02 s at 22 050 Hz)
 ZC = 441
@@ -354,10 +354,12 @@ def run_ours(a):
             return cfm.solve_euler(z_d, lens, prompt_d, mu_d, style_d, t_span, list(cfg), False)
         return cfm.solve_euler(z_d, lens, prompt_d, mu_d, style_d, None, t_span, cfg)
 
+    voc_chunk = max(1, VOC_FRAMES // gen)
+
     def vocode(mel):
-        if mel.shape[0] <= VOC_CHUNK:
+        if mel.shape[0] <= voc_chunk:
             return voc(mel)
-        return torch.cat([voc(mel[i:i + VOC_CHUNK]) for i in range(0, mel.shape[0], VOC_CHUNK)])
+        return torch.cat([voc(mel[i:i + voc_chunk]) for i in range(0, mel.shape[0], voc_chunk)])
 
     def convert_eager(mu_d, prompt_d, style_d, z_d, lens):
         return vocode(sample(mu_d, prompt_d, style_d, z_d, lens)[:, :, Tp:].contiguous())

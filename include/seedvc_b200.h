@@ -100,6 +100,9 @@ typedef struct svc_gemm_desc {
        path rotate in the accumulator's row layout with coalesced table reads.  NULL = not given. */
     const float* rope_tab_t;
     int rope_ld;
+    /* element type of out_op when it differs from the operands': 0 = same as dtype, else 1 + SVC_BF16 / SVC_F16
+       (a bf16 GEMM may write an fp16 operand copy and vice versa; fp32 GEMMs write fp32). */
+    int out_op_dtype_p1;
 } svc_gemm_desc;
 
 int svc_gemm(const svc_gemm_desc* d, int backend, void* stream);

@@ -109,10 +109,14 @@ def load():
     from modules.length_regulator import InterpolateRegulator  # noqa: E402
     from modules.audio import mel_spectrogram  # noqa: E402
     from modules.v2.length_regulator import InterpolateRegulator as InterpolateRegulatorV2  # noqa: E402
+    from modules.hifigan.generator import HiFTGenerator  # noqa: E402
+    from modules.hifigan.f0_predictor import ConvRNNF0Predictor  # noqa: E402
+    import modules.hifigan.generator as hift_module  # noqa: E402
 
     ns = types.SimpleNamespace(
         CFM=CFM, DiT=DiT, BigVGAN=BigVGAN, BigVGANAttrDict=BigVGANAttrDict,
         Activation1d=Activation1d, SnakeBeta=SnakeBeta, Snake=Snake,
         CFMv2=CFMv2, DiTv2=DiTv2, WN=WN, InterpolateRegulator=InterpolateRegulator, mel_spectrogram=mel_spectrogram, InterpolateRegulatorV2=InterpolateRegulatorV2,
+        HiFTGenerator=HiFTGenerator, ConvRNNF0Predictor=ConvRNNF0Predictor, hift_module=hift_module,
     )
     return ns

@@ -581,3 +581,143 @@ def sola_step(infer_wav, sola_buffer, fade_in_window, fade_out_window, sola_buff
     new_buffer = infer_wav[block_frame:block_frame + sola_buffer_frame].clone()               # :1135-1137
     return infer_wav[:block_frame].clone(), new_buffer, sola_offset
 
+
+
+# ---------------------------------------------------------------------------------------------
+# HiFT vocoder: modules/hifigan/generator.py:282-454, f0_predictor.py:19-55,
+# configs/hifigan.yml.  The two random draws of SineGen (:222-236) are INPUTS here so the same noise can be
+# injected into every implementation: ``phase`` (B, nb_harmonics + 1, 1) and ``noise`` (B, nb_harmonics + 1, L)
+# standard normal; the third draw (SourceModuleHnNSF.forward's noise branch, :277-278) never reaches the output.
+# ---------------------------------------------------------------------------------------------
+HIFT_CFG = dict(in_channels=80, base_channels=512, nb_harmonics=8, sampling_rate=22050, nsf_alpha=0.1,
+                nsf_sigma=0.003, nsf_voiced_threshold=10, upsample_rates=[8, 8], upsample_kernel_sizes=[16, 16],
+                n_fft=16, hop_len=4, resblock_kernel_sizes=[3, 7, 11],
+                resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], source_resblock_kernel_sizes=[7, 11],
+                source_resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]], lrelu_slope=0.1, audio_limit=0.99)
+
+
+def hift_f0_predictor(sd, mel, pfx="f0_predictor."):
+    """ConvRNNF0Predictor.forward (f0_predictor.py:52-55): 5 x [weight-normed Conv1d k3 + ELU], Linear, abs."""
+    x = mel
+    for i in range(5):
+        x = F.elu(F.conv1d(x, _wn_weight(sd, f"{pfx}condnet.{2 * i}"), sd[f"{pfx}condnet.{2 * i}.bias"], padding=1))
+    return torch.abs(_linear(sd, pfx + "classifier", x.transpose(1, 2)).squeeze(-1))
+
+
+def hift_source(sd, f0, phase, noise, cfg=HIFT_CFG):
+    """_f02source (:366-370) -> SourceModuleHnNSF.forward (:262-279) -> SineGen.forward (:208-243).
+    f0 (B, Tm) Hz -> harmonic source (B, L), L = Tm * prod(upsample_rates) * hop_len."""
+    scale = int(np.prod(cfg["upsample_rates"])) * cfg["hop_len"]
+    f0u = f0[:, None].repeat_interleave(scale, dim=-1)               # nn.Upsample(nearest), (B, 1, L)
+    H = cfg["nb_harmonics"] + 1
+    F_mat = torch.cat([f0u * (i + 1) / cfg["sampling_rate"] for i in range(H)], dim=1)     # (B, H, L)
+    theta = 2 * np.pi * (torch.cumsum(F_mat, dim=-1) % 1)
+    ph = phase.clone()
+    ph[:, 0, :] = 0
+    sine = cfg["nsf_alpha"] * torch.sin(theta + ph)
+    uv = (f0u > cfg["nsf_voiced_threshold"]).float()
+    noise_amp = uv * cfg["nsf_sigma"] + (1 - uv) * cfg["nsf_alpha"] / 3
+    sine = sine * uv + noise_amp * noise
+    merged = torch.tanh(_linear(sd, "m_source.l_linear", sine.transpose(1, 2)))            # (B, L, 1)
+    return merged[..., 0]
+
+
+def _hann_periodic(n):
+    return torch.hann_window(n, periodic=True)
+
+
+def hift_stft(x, n_fft=16, hop=4):
+    """torch.stft(center=True, reflect, onesided) written out (:372-378): (B, L) -> real, imag (B, n_fft/2+1, L/hop+1)."""
+    xp = F.pad(x[:, None], (n_fft // 2, n_fft // 2), mode="reflect")[:, 0]
+    frames = xp.unfold(-1, n_fft, hop) * _hann_periodic(n_fft)       # (B, TT, n_fft)
+    k = torch.arange(n_fft // 2 + 1, dtype=torch.float64)[:, None]
+    n = torch.arange(n_fft, dtype=torch.float64)[None, :]
+    ang = 2 * math.pi * k * n / n_fft
+    re = frames @ torch.cos(ang).float().t()
+    im = frames @ (-torch.sin(ang)).float().t()
+    return re.transpose(1, 2), im.transpose(1, 2)
+
+
+def hift_istft(mag, phase, n_fft=16, hop=4):
+    """_istft (:380-385): clip, polar -> torch.istft(center=True) written out as windowed irfft + overlap-add /
+    window envelope.  mag, phase (B, n_fft/2+1, TT) -> (B, hop * (TT - 1))."""
+    mag = torch.clip(mag, max=1e2)
+    re, im = mag * torch.cos(phase), mag * torch.sin(phase)
+    B, nb, TT = re.shape
+    k = torch.arange(nb, dtype=torch.float64)[:, None]
+    n = torch.arange(n_fft, dtype=torch.float64)[None, :]
+    ang = 2 * math.pi * k * n / n_fft
+    wk = torch.full((nb, 1), 2.0, dtype=torch.float64)
+    wk[0] = wk[-1] = 1.0                                             # c2r: DC / Nyquist once, their imag ignored
+    C = (wk * torch.cos(ang) / n_fft).float()
+    S = (-wk * torch.sin(ang) / n_fft).float()
+    w = _hann_periodic(n_fft)
+    fr = (re.transpose(1, 2) @ C + im.transpose(1, 2) @ S) * w       # (B, TT, n_fft)
+    total = n_fft + hop * (TT - 1)
+    y = torch.zeros(B, total)
+    env = torch.zeros(total)
+    for t in range(TT):
+        y[:, t * hop:t * hop + n_fft] += fr[:, t]
+        env[t * hop:t * hop + n_fft] += w * w
+    half = n_fft // 2
+    return y[:, half:total - half] / env[half:total - half]
+
+
+def _hift_snake(x, alpha):
+    """Snake (generator.py:79-90), linear-scale alpha."""
+    a = alpha.view(1, -1, 1)
+    return x + (1.0 / (a + 1e-9)) * torch.sin(x * a) ** 2
+
+
+def _hift_resblock(sd, pfx, x, k, dils):
+    """ResBlock.forward (:151-158)."""
+    for i, d in enumerate(dils):
+        xt = _hift_snake(x, sd[f"{pfx}.activations1.{i}.alpha"])
+        xt = F.conv1d(xt, _wn_weight(sd, f"{pfx}.convs1.{i}"), sd[f"{pfx}.convs1.{i}.bias"], dilation=d,
+                      padding=d * (k - 1) // 2)
+        xt = _hift_snake(xt, sd[f"{pfx}.activations2.{i}.alpha"])
+        xt = F.conv1d(xt, _wn_weight(sd, f"{pfx}.convs2.{i}"), sd[f"{pfx}.convs2.{i}.bias"], padding=(k - 1) // 2)
+        x = xt + x
+    return x
+
+
+def hift_forward(sd, mel, phase, noise, f0=None, cfg=HIFT_CFG):
+    """HiFTGenerator.forward (:387-436).  mel (B, 80, Tm) -> waveform (B, 256 * Tm)."""
+    if f0 is None:
+        f0 = hift_f0_predictor(sd, mel)
+    s = hift_source(sd, f0, phase, noise, cfg)
+    re, im = hift_stft(s, cfg["n_fft"], cfg["hop_len"])
+    s_stft = torch.cat([re, im], dim=1)
+    nk, nu = len(cfg["resblock_kernel_sizes"]), len(cfg["upsample_rates"])
+    down = [1] + cfg["upsample_rates"][::-1][:-1]
+    down_cum = list(np.cumprod(down))[::-1]                          # [8, 1]
+    x = F.conv1d(mel, _wn_weight(sd, "conv_pre"), sd["conv_pre.bias"], padding=3)
+    for i in range(nu):
+        u, k = cfg["upsample_rates"][i], cfg["upsample_kernel_sizes"][i]
+        x = F.leaky_relu(x, cfg["lrelu_slope"])
+        x = F.conv_transpose1d(x, _wn_weight_convT(sd, f"ups.{i}"), sd[f"ups.{i}.bias"], stride=u,
+                               padding=(k - u) // 2)
+        if i == nu - 1:
+            x = F.pad(x, (1, 0), mode="reflect")
+        r = int(down_cum[i])
+        if r == 1:
+            si = F.conv1d(s_stft, sd[f"source_downs.{i}.weight"], sd[f"source_downs.{i}.bias"])
+        else:
+            si = F.conv1d(s_stft, sd[f"source_downs.{i}.weight"], sd[f"source_downs.{i}.bias"], stride=r,
+                          padding=r // 2)
+        si = _hift_resblock(sd, f"source_resblocks.{i}", si, cfg["source_resblock_kernel_sizes"][i],
+                            cfg["source_resblock_dilation_sizes"][i])
+        x = x + si
+        xs = None
+        for j in range(nk):
+            y = _hift_resblock(sd, f"resblocks.{i * nk + j}", x, cfg["resblock_kernel_sizes"][j],
+                               cfg["resblock_dilation_sizes"][j])
+            xs = y if xs is None else xs + y
+        x = xs / nk
+    x = F.leaky_relu(x)                                              # default slope 0.01 (:424)
+    x = F.conv1d(x, _wn_weight(sd, "conv_post"), sd["conv_post.bias"], padding=3)
+    nb = cfg["n_fft"] // 2 + 1
+    mag = torch.exp(x[:, :nb])
+    ph = torch.sin(x[:, nb:])
+    y = hift_istft(mag, ph, cfg["n_fft"], cfg["hop_len"])
+    return torch.clamp(y, -cfg["audio_limit"], cfg["audio_limit"])

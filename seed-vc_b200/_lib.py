@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
         ("alpha", c_float), ("accumulate", c_int),
         ("out_f32", c_vp), ("of_bstride", c_ll), ("of_rstride", c_ll),
         ("out_op", c_vp), ("oo_bstride", c_ll), ("oo_rstride", c_ll),
-        ("rope_tab_t", c_vp), ("rope_ld", c_int),
+        ("rope_tab_t", c_vp), ("rope_ld", c_int), ("out_op_dtype_p1", c_int),
     ]
 
 

@@ -63,7 +63,7 @@ inline EpiParams make_epi_params(const svc_gemm_desc& d) {
     e.oo_bstride = d.oo_bstride;
     e.oo_rstride = d.oo_rstride;
     e.op_is_f32 = d.dtype == SVC_F32;
-    e.op_is_f16 = d.dtype == SVC_F16;
+    e.op_is_f16 = (d.out_op_dtype_p1 > 0 ? d.out_op_dtype_p1 - 1 : d.dtype) == SVC_F16;
     auto al = [](const void* p, long long s0, long long s1, int esz) {
         return p == nullptr || ((reinterpret_cast<uintptr_t>(p) % 16 == 0) &&
                                 ((s0 * esz) % 16 == 0) && ((s1 * esz) % 16 == 0));

@@ -40,6 +40,7 @@ struct alignas(64) TcParams {
     TcSeg seg[SVC_MAX_SEG];
     int n_seg, total_kb;
     int B, T, tiles_per_batch, n_tiles;
+    int ab_f16;                // operands are IEEE half (else bf16)
 #ifdef SVC_TRACE
     int dbg;   // trace builds only (SVC_DBG env): 1 = skip epilogue body, 2 = skip MMA issue (timing experiments)
 #endif
@@ -680,7 +681,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 const int n0 = (tile % p.n_tiles) * BN;
                 int n_umma = p.epi.N - n0;
                 n_umma = n_umma > BN ? BN : ((n_umma + 15) & ~15);
-                const uint32_t idesc = umma_idesc_bf16(BM, n_umma, 0, 0, p.epi.op_is_f16 ? 0u : 1u);
+                const uint32_t idesc = umma_idesc_bf16(BM, n_umma, 0, 0, p.ab_f16 ? 0u : 1u);
                 const int acc = it & 1;
                 GTRACE(1, it, 0);
                 mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);   // epilogue drained this buffer
@@ -1128,6 +1129,7 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
     p.dbg = dbg;
 #endif
     p.n_seg = d.n_seg;
+    p.ab_f16 = d.dtype == SVC_F16;
     p.total_kb = total_kb;
     p.B = d.B;
     p.T = d.T;
@@ -1224,6 +1226,11 @@ extern "C" int svc_gemm(const svc_gemm_desc* d, int backend, void* stream) {
     }
     if ((d->act == SVC_ACT_SWIGLU_PAIR || d->act == SVC_ACT_TANH_SIG_PAIR) && (d->N % 2)) {
         svc_set_error("svc_gemm: pair activation needs even N");
+        return SVC_ERR_ARG;
+    }
+    if (d->out_op_dtype_p1 != 0 &&
+        (d->dtype == SVC_F32 || (d->out_op_dtype_p1 - 1 != SVC_BF16 && d->out_op_dtype_p1 - 1 != SVC_F16))) {
+        svc_set_error("svc_gemm: out_op_dtype_p1 must name a 16-bit type and needs 16-bit operands");
         return SVC_ERR_ARG;
     }
     if (d->out_f32 == nullptr && d->out_op == nullptr) {

@@ -101,6 +101,7 @@ class DiTEngine:
         sp, ops = self.spec, self.ops
         p = sp.prefix
         od = ops.op_dtype
+        sdt = ops.stream_dtype        # operands that carry a residual stream (see Ops.stream_dtype)
         D, L, C = sp.D, sp.L, sp.C
 
         def dev(t, dtype=None):
@@ -137,7 +138,7 @@ class DiTEngine:
                     add_ada(f"ffn{i}", sd[lp + "ffn_norm.project_layer.weight"],
                             sd[lp + "ffn_norm.project_layer.bias"])
                 if sp.uvit and i > L // 2:
-                    sk = dev(sd[lp + "skip_in_linear.weight"], od)
+                    sk = dev(sd[lp + "skip_in_linear.weight"], sdt)
                     lw["skip_w"] = sk
                     lw["skip_b"] = dev(sd[lp + "skip_in_linear.bias"])
             else:
@@ -174,10 +175,10 @@ class DiTEngine:
         half = 128
         w["freqs"] = dev(torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half))
 
-        w["cond_w"] = dev(sd[p + "cond_projection.weight"], od)
+        w["cond_w"] = dev(sd[p + "cond_projection.weight"], sdt)
         w["cond_b"] = dev(sd[p + "cond_projection.bias"])
         mw = sd[p + "cond_x_merge_linear.weight"].float()
-        w["merge_w"] = dev(mw, od)                       # column blocks are taken as views
+        w["merge_w"] = dev(mw, sdt)                      # column blocks are taken as views
         w["merge_b"] = dev(sd[p + "cond_x_merge_linear.bias"])
         # null-branch constant of the content columns: W_c @ b_cond (fp32, exact)
         Wc = mw[:, 2 * C:2 * C + D]
@@ -188,22 +189,22 @@ class DiTEngine:
             w["style_in_w"] = dev(sd[p + "style_in.weight"])
             w["style_in_b"] = dev(sd[p + "style_in.bias"])
         if sp.long_skip:
-            w["lskip_w"] = dev(sd[p + "skip_linear.weight"], od)
+            w["lskip_w"] = dev(sd[p + "skip_linear.weight"], sdt)
             w["lskip_b"] = dev(sd[p + "skip_linear.bias"])
         if sp.head == "mlp":
-            w["mlp0_w"] = dev(sd[p + "final_mlp.0.weight"], od)
+            w["mlp0_w"] = dev(sd[p + "final_mlp.0.weight"], sdt)
             w["mlp0_b"] = dev(sd[p + "final_mlp.0.bias"])
-            w["mlp2_w"] = dev(sd[p + "final_mlp.2.weight"], od)
+            w["mlp2_w"] = dev(sd[p + "final_mlp.2.weight"], sdt)
             w["mlp2_b"] = dev(sd[p + "final_mlp.2.bias"])
         else:
             Dw, nl, ks = sp.Dw, sp.wn_layers, sp.wn_kernel
-            w["conv1_w"] = dev(sd[p + "conv1.weight"], od)
+            w["conv1_w"] = dev(sd[p + "conv1.weight"], sdt)
             w["conv1_b"] = dev(sd[p + "conv1.bias"])
-            w["resp_w"] = dev(sd[p + "res_projection.weight"], od)
+            w["resp_w"] = dev(sd[p + "res_projection.weight"], sdt)
             w["resp_b"] = dev(sd[p + "res_projection.bias"])
-            w["conv2_w"] = dev(sd[p + "conv2.weight"].float().reshape(C, Dw), od)
+            w["conv2_w"] = dev(sd[p + "conv2.weight"].float().reshape(C, Dw), sdt)
             w["conv2_b"] = dev(sd[p + "conv2.bias"])
-            w["fl_w"] = dev(_fold_wn(sd, p + "final_layer.linear"), od)
+            w["fl_w"] = dev(_fold_wn(sd, p + "final_layer.linear"), sdt)
             w["fl_b"] = dev(sd[p + "final_layer.linear.bias"])
             cw = _fold_wn(sd, p + "wavenet.cond_layer.conv.conv").reshape(2 * Dw * nl, Dw)
             cb = sd[p + "wavenet.cond_layer.conv.conv.bias"].float()
@@ -221,8 +222,8 @@ class DiTEngine:
                 wr = wr.reshape(wr.shape[0], Dw)
                 br = sd[f"{p}wavenet.res_skip_layers.{l}.conv.conv.bias"].float()
                 wn.append({
-                    "in_w": dev(wi.permute(2, 0, 1), od),                      # (k, 2Dw, Dw)
-                    "rs_w": dev(wr, od), "rs_b": dev(br),
+                    "in_w": dev(wi.permute(2, 0, 1), sdt),                     # (k, 2Dw, Dw)
+                    "rs_w": dev(wr, sdt), "rs_b": dev(br),
                     "rs_b_res": dev(br[:Dw]), "rs_b_skip": dev(br[Dw:]),
                 })
             w["wn"] = wn
@@ -237,7 +238,7 @@ class DiTEngine:
                 br = sd[f"{p}wavenet.res_skip_layers.{l}.conv.conv.bias"].float()
                 skip_w.append(wr[Dw:] if l < nl - 1 else wr)
                 skip_b += br[Dw:] if l < nl - 1 else br
-            w["wn_skip_w"] = dev(torch.cat(skip_w, 1), od)                     # (Dw, nl*Dw)
+            w["wn_skip_w"] = dev(torch.cat(skip_w, 1), sdt)                    # (Dw, nl*Dw)
             w["wn_skip_b"] = dev(skip_b)
         self.w = w
 
@@ -309,9 +310,10 @@ class DiTEngine:
             st["wn_g"] = g[0]                              # (N, nl*2Dw), conv bias included
 
         # ---- step-invariant part of cond_x_merge_linear ----------------------------------
-        mu_op = ops.empty(B, T, sp.content_dim, device=dev)
+        sdt = ops.stream_dtype
+        mu_op = ops.empty(B, T, sp.content_dim, device=dev, dtype=sdt)
         ops.cast(mu.contiguous(), mu_op)
-        cond_op = ops.empty(B, T, D, device=dev)
+        cond_op = ops.empty(B, T, D, device=dev, dtype=sdt)
         ops.gemm([(mu_op, 0, w["cond_w"])], D, B=B, T=T, bias=w["cond_b"], out_op=cond_op)
         mw = w["merge_w"]
         Wx, Wp, Wc = mw[:, :C], mw[:, C:2 * C], mw[:, 2 * C:2 * C + D]
@@ -370,22 +372,24 @@ class DiTEngine:
         st["qkv"] = torch.empty(R, Tq, 3 * D, dtype=od, device=dev)
         st["att"] = torch.empty(R, Tq, D, dtype=od, device=dev)
         st["ff"] = torch.empty(R, Tq, sp.I, dtype=od, device=dev)
-        st["h_op"] = torch.empty(R, Tq, D, dtype=od, device=dev)
+        st["h_op"] = torch.empty(R, Tq, D, dtype=sdt, device=dev)
+        # output of the final norm: input of the head chain (stream dtype); aliases xn when the dtypes agree
+        st["xn_f"] = st["xn"] if sdt == od else torch.empty(R, Tq, D, dtype=sdt, device=dev)
         n_skip = L // 2 if sp.uvit else 0
-        st["skips"] = [torch.empty(R, Tq, D, dtype=od, device=dev) for _ in range(n_skip)]
+        st["skips"] = [torch.empty(R, Tq, D, dtype=sdt, device=dev) for _ in range(n_skip)]
         st["v"] = torch.empty(R, T, C, dtype=f32, device=dev)
         if sp.long_skip:
-            st["x_res"] = torch.empty(R, T, D, dtype=od, device=dev)
+            st["x_res"] = torch.empty(R, T, D, dtype=sdt, device=dev)
         if sp.head == "mlp":
-            st["y"] = torch.empty(R, T, D, dtype=od, device=dev)
+            st["y"] = torch.empty(R, T, D, dtype=sdt, device=dev)
         else:
             Dw, pad = sp.Dw, (sp.wn_kernel - 1) // 2
             st["xw"] = torch.empty(R, T, Dw, dtype=f32, device=dev)
-            st["xw_op"] = torch.zeros(R, T + 2 * pad, Dw, dtype=od, device=dev)
-            st["acts"] = torch.empty(R, T, sp.wn_layers * Dw, dtype=od, device=dev)
+            st["xw_op"] = torch.zeros(R, T + 2 * pad, Dw, dtype=sdt, device=dev)
+            st["acts"] = torch.empty(R, T, sp.wn_layers * Dw, dtype=sdt, device=dev)
             st["wn_out"] = torch.empty(R, T, Dw, dtype=f32, device=dev)
-            st["ln"] = torch.empty(R, T, Dw, dtype=od, device=dev)
-            st["y"] = torch.empty(R, T, Dw, dtype=od, device=dev)
+            st["ln"] = torch.empty(R, T, Dw, dtype=sdt, device=dev)
+            st["y"] = torch.empty(R, T, Dw, dtype=sdt, device=dev)
             st["wn_lens"] = st["x_lens"].repeat(nb).contiguous()
         self.st = st
         return st
@@ -462,7 +466,8 @@ class DiTEngine:
                 ops.norm_mod(h, xn, gamma=lw["g_ffn"], mul=a[4 * D:5 * D], add=a[3 * D:4 * D])
             ops.gemm([(xn, 0, lw["w13"])], 2 * sp.I, B=R, T=Tq, act=ACT_SWIGLU_PAIR, out_op=ff)
             out_op = None
-            if i in emit and sp.version == 1 and (i + 1) < L and (i + 1) not in recv:
+            if i in emit and sp.version == 1 and (i + 1) < L and (i + 1) not in recv and \
+                    ops.stream_dtype == ops.op_dtype:
                 pending_raw = skip_bufs.pop(0)       # filled by layer i+1's attention norm
                 skips.append(pending_raw)
             elif i in emit:
@@ -472,12 +477,9 @@ class DiTEngine:
                 out_op = st["h_op"]
             ops.gemm([(ff, 0, lw["w2"])], D, B=R, T=Tq, gate=gate_m, res=h, out_f32=h, out_op=out_op)
         # ---- final norm (uses c even when time is a token, diffusion_transformer.py:142) ----
-        a = self._ada(s, "final")
-        if sp.version == 1:
-            ops.norm_mod(h, xn, gamma=w["g_final"], mul=a[:D], add=a[D:])
-        else:
-            ops.norm_mod(h, xn, gamma=w["g_final"], mul=a[:D], add=a[D:])   # (1+scale), shift
-        xf = xn[:, ntok:, :]
+        a = self._ada(s, "final")         # v1: w, b of the AdaLN projection; v2: (1 + scale), shift
+        ops.norm_mod(h, st["xn_f"], gamma=w["g_final"], mul=a[:D], add=a[D:])
+        xf = st["xn_f"][:, ntok:, :]
         v = st["v"]
         if sp.long_skip:     # skip_linear(cat[x_res, x]) without the concat (:524-525)
             lw_, lb_ = w["lskip_w"], w["lskip_b"]

@@ -229,9 +229,9 @@ class DiT(nn.Module):
         x_lens = x_lens.to(dev)
         if x_lens.numel() == 1 and N > 1:
             x_lens = x_lens.expand(N)
-        prompt_op = ops.empty(N, T, C, device=dev)
+        prompt_op = ops.empty(N, T, C, device=dev, dtype=ops.stream_dtype)
         ops.bct_to_btc(prompt_x.float().contiguous(), prompt_op)
-        x_op = ops.empty(N, T, C, device=dev)
+        x_op = ops.empty(N, T, C, device=dev, dtype=ops.stream_dtype)
         ops.bct_to_btc(x.float().contiguous(), x_op)
         eng.begin([(True, True, True)], prompt_op, cond.float(), style.float(), x_lens,
                   t[:1].detach().float().cpu())
@@ -298,9 +298,9 @@ class BASECFM(nn.Module):
         # frames-major state: x fp32 master + operand copy; prompt region zeroed
         xs = torch.empty(B, T, C, dtype=torch.float32, device=dev)
         ops.bct_to_btc(x.float().contiguous(), xs, zero_from=0, zero_to=Tp)
-        x_op = ops.empty(B, T, C, device=dev)
+        x_op = ops.empty(B, T, C, device=dev, dtype=ops.stream_dtype)
         ops.bct_to_btc(x.float().contiguous(), x_op, zero_from=0, zero_to=Tp)
-        prompt_op = ops.zeros(B, T, C, device=dev)
+        prompt_op = ops.zeros(B, T, C, device=dev, dtype=ops.stream_dtype)
         if Tp > 0:
             ops.bct_to_btc(prompt[..., :Tp].float().contiguous(), prompt_op[:, :Tp, :])
         st = eng.begin(branches, prompt_op, mu.float(), style.float(), x_lens,

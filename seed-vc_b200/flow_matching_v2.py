@@ -113,9 +113,9 @@ class DiT(nn.Module):
         dev = x.device
         if not bool((t == t[0]).all()):
             raise NotImplementedError("rows of one estimator call must share the timestep")
-        prompt_op = ops.empty(N, T, C, device=dev)
+        prompt_op = ops.empty(N, T, C, device=dev, dtype=ops.stream_dtype)
         ops.bct_to_btc(prompt_x.float().contiguous(), prompt_op)
-        x_op = ops.empty(N, T, C, device=dev)
+        x_op = ops.empty(N, T, C, device=dev, dtype=ops.stream_dtype)
         ops.bct_to_btc(x.float().contiguous(), x_op)
         eng.begin([(True, True, True)], prompt_op, cond.float(), style.float(), x_lens.to(dev),
                   t[:1].detach().float().cpu())
@@ -178,9 +178,9 @@ class CFM(nn.Module):
             branches, coefs = [full, txt, null], [1.0 + w0 + w1, -w1, -w0]
         xs = torch.empty(B, T, C, dtype=torch.float32, device=dev)
         ops.bct_to_btc(x.float().contiguous(), xs, zero_from=0, zero_to=Tp)
-        x_op = ops.empty(B, T, C, device=dev)
+        x_op = ops.empty(B, T, C, device=dev, dtype=ops.stream_dtype)
         ops.bct_to_btc(x.float().contiguous(), x_op, zero_from=0, zero_to=Tp)
-        prompt_op = ops.zeros(B, T, C, device=dev)
+        prompt_op = ops.zeros(B, T, C, device=dev, dtype=ops.stream_dtype)
         if Tp > 0:
             ops.bct_to_btc(prompt[..., :Tp].float().contiguous(), prompt_op[:, :Tp, :])
         st = eng.begin(branches, prompt_op, mu.float(), style.float(), x_lens.to(dev),

@@ -33,6 +33,12 @@ class Ops:
         self.lib = _lib.load_library()
         self.mode = mode
         self.op_dtype, self.op_code = MODES[mode]
+        # dtype of operands that carry a residual STREAM itself (U-ViT skip tensors, long skip, head chain, the
+        # x / prompt / content inputs) rather than a normalised branch input.  In bf16 mode these are IEEE half:
+        # rounding the stream to 8 mantissa bits is the largest single error source of the bf16 path (measured,
+        # scripts/analysis/bf16_ablation.py), the GEMMs that read them are a few % of the FLOPs, and both formats
+        # run on the same tcgen05 kind::f16 path.
+        self.stream_dtype = torch.float16 if mode == "bf16" else self.op_dtype
         self.backend = BACKEND_SIMT if force_simt else BACKEND_AUTO
         self.precise = 1 if mode == "fp32" else 0
         self.launches = 0
@@ -105,8 +111,10 @@ class Ops:
         ``f32=True`` forces fp32 operands whatever the mode (small conditioning GEMMs).
         """
         d = GemmDesc()
-        dt = torch.float32 if f32 else self.op_dtype
-        d.dtype = SVC_F32 if f32 else self.op_code
+        dt = segs[0][0].dtype              # operand type of this call: fp32, or one of the 16-bit formats
+        if f32:
+            assert dt == torch.float32
+        d.dtype = self._code(dt)
         d.B, d.T, d.N, d.n_seg = B, T, N, len(segs)
         for i, (A, shift, W) in enumerate(segs):
             self._chk(A, W)
@@ -152,11 +160,14 @@ class Ops:
             d.out_f32 = out_f32.data_ptr()
             d.of_bstride, d.of_rstride = out_f32.stride(0), out_f32.stride(1)
         if out_op is not None:
-            assert out_op.dtype == dt and out_op.shape == (B, T, n_out) and out_op.stride(2) == 1
+            assert out_op.shape == (B, T, n_out) and out_op.stride(2) == 1
+            if out_op.dtype != dt:         # 16-bit operand copy in the other 16-bit format
+                assert dt != torch.float32 and out_op.dtype in (torch.bfloat16, torch.float16)
+                d.out_op_dtype_p1 = 1 + self._code(out_op.dtype)
             d.out_op = out_op.data_ptr()
             d.oo_bstride, d.oo_rstride = out_op.stride(0), out_op.stride(1)
         ktot = sum(W.shape[1] for _, _, W in segs)
-        cat = "gemm_f32" if (f32 or self.mode == "fp32") else ("gemm_tc" if self.backend == BACKEND_AUTO
+        cat = "gemm_f32" if dt == torch.float32 else ("gemm_tc" if self.backend == BACKEND_AUTO
                                                                else "gemm_simt")
         # algo_flops: algorithmic work when the launch computes a zero-padded regrouping
         self._t0(cat, 2.0 * B * T * N * ktot if algo_flops is None else float(algo_flops))

@@ -33,14 +33,20 @@ def synth_tensor(name: str, shape, seed: int = 0) -> torch.Tensor:
     g = _gen(name, seed)
     shape = tuple(shape)
     leaf = name.split(".")[-1]
+    if name == "conv_post.weight_g":            # HiFT: keeps exp(magnitude rows) O(0.2) so the +-0.99 clamp is rare
+        return 0.35 + 0.3 * torch.rand(shape, generator=g)
     if leaf == "weight_g":                      # weight-norm gain == row norm of w
         return 0.7 + 0.6 * torch.rand(shape, generator=g)
+    if leaf == "alpha" and (".activations1." in name or ".activations2." in name):
+        return (1.0 + 0.25 * _randn(shape, g)).clamp_min(0.3)     # HiFT Snake: linear-scale alpha around 1
     if leaf in ("alpha", "beta"):               # Snake, log scale
         return 0.3 * _randn(shape, g)
     if leaf == "bias":
         b = 0.1 * _randn(shape, g)
         if name.endswith("project_layer.bias"):  # v1 AdaLN: first half multiplies the norm
             b[: shape[0] // 2] += 1.0
+        if name == "conv_post.bias" and shape[0] == 18:   # HiFT: log-magnitude rows centred at -1.5
+            b[:9] -= 1.5
         return b
     if len(shape) == 1:                          # RMSNorm weights
         return 1.0 + 0.1 * _randn(shape, g)
@@ -90,6 +96,26 @@ def synth_batch(B: int, T: int, Tp: int, n_mels: int, content_dim: int,
     style = torch.stack([p[2] for p in parts])
     z = torch.stack([p[3] for p in parts])
     return mu, prompt, style, z
+
+
+def synth_f0(B: int, Tm: int, seed: int = 3) -> torch.Tensor:
+    """Frame-rate F0 track in Hz with voiced runs (80-400 Hz, slowly varying) and unvoiced gaps (0)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    base = 80.0 + 320.0 * torch.rand(B, 1, generator=g)
+    wob = torch.cumsum(4.0 * torch.randn(B, Tm, generator=g), dim=1)
+    f0 = (base + wob).clamp_(60.0, 500.0)
+    seg = (torch.arange(Tm)[None, :] // 9 + torch.randint(0, 4, (B, 1), generator=g)) % 4
+    return torch.where(seg == 3, torch.zeros_like(f0), f0)
+
+
+def synth_hift_noise(B: int, H: int, L: int, seed: int = 5):
+    """The two random draws of HiFT's SineGen, made reproducible: phase (B, H, 1) in [-pi, pi), noise (B, H, L)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    phase = (torch.rand(B, H, 1, generator=g) * 2 - 1) * math.pi
+    noise = torch.randn(B, H, L, generator=g)
+    return phase, noise
 
 
 def synth_mel(B: int, n_mels: int, Tm: int, seed: int = 7) -> torch.Tensor:

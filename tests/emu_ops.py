@@ -18,6 +18,7 @@ class EmuOps:
     def __init__(self, mode="fp32"):
         self.mode = "fp32"
         self.op_dtype = torch.float32
+        self.stream_dtype = torch.float32
         self.launches = 0
 
     def empty(self, *shape, dtype=None, device="cpu"):

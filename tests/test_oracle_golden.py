@@ -224,3 +224,20 @@ def test_oracle_bigvgan_full_size_256(manifest):
     sd = synth.synth_state_dict(manifest["keys_" + m["config"]])
     wav = orc.bigvgan_forward(sd, h, synth.synth_mel(m["B"], h.num_mels, m["Tm"], seed=m["mel_seed"]))
     assert rel_l2(wav[:, :, torch.from_numpy(g["idx"])], g["wav"]) < 2e-5
+
+
+@pytest.mark.parametrize("sr,n_fft,n_mels,fmin,fmax", [(22050, 1024, 80, 0, None), (44100, 2048, 128, 0, None),
+                                                        (22050, 1024, 80, 0, 8000), (16000, 400, 80, 0, 8000)])
+def test_mel_filterbank_pinned_to_torchaudio(sr, n_fft, n_mels, fmin, fmax):
+    """SURVEY 8f N3 pin: librosa is not installed, so the Slaney filterbank that stands in for
+    ``librosa.filters.mel`` (modules/audio.py:4,66) - the oracle's restatement AND the package's own - is pinned to an
+    independent published implementation, torchaudio's ``melscale_fbanks(norm='slaney', mel_scale='slaney')``."""
+    ta = pytest.importorskip("torchaudio")
+    from seedvc_b200 import audio
+    want = ta.functional.melscale_fbanks(n_fft // 2 + 1, float(fmin), float(fmax if fmax else sr / 2), n_mels, sr,
+                                         norm="slaney", mel_scale="slaney").t()
+    got_o = torch.as_tensor(orc.slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax)).float()
+    got_p = torch.as_tensor(audio.mel_filterbank(sr, n_fft, n_mels, fmin, fmax)).float().cpu()
+    assert got_o.shape == want.shape == got_p.shape
+    assert float((got_o - want).abs().max()) < 2e-7 and rel_l2(got_o, want) < 1e-5
+    assert float((got_p - want).abs().max()) < 2e-7 and rel_l2(got_p, want) < 1e-5
