@@ -48,6 +48,9 @@ WORKLOADS = {
                     cfg=(0.7, 0.7), scaling="strong"),
     "config5": dict(kind="stream", model="xlsr_tiny", voc="bigvgan_22k", B=512, T=323, Tp=258, steps=10, cfg=0.7,
                     scaling="weak", graph=True),
+    # config 5 with the vocoder the released xlsr-tiny model is trained against (HiFT)
+    "config5_hift": dict(kind="stream", model="xlsr_tiny", voc="hift", B=512, T=323, Tp=258, steps=10, cfg=0.7,
+                         scaling="weak", graph=True),
     "smoke": dict(kind="v1", model="whisper_small", voc="bigvgan_22k", B=2, T=323, Tp=65, steps=4, cfg=0.7,
                   scaling="weak"),
     "profile": dict(kind="v1", model="whisper_small", voc="bigvgan_22k", B=8, T=2580, Tp=430, steps=2, cfg=0.7,
@@ -58,6 +61,11 @@ VOC_FRAMES = 32 * 2150    # mel frames per vocoder call (bounds the stage buffer
 # extra_right 0.02 s at 22 050 Hz)
 ZC = 441
 STREAM = dict(block=9 * ZC, sola_buffer=2 * ZC, sola_search=ZC, tail=1 * ZC, tick_s=0.18)
+
+
+def voc_spec(name):
+    """(hop, sampling rate, mel bins) of a vocoder."""
+    return (512, 44100, 128) if name == "bigvgan_44k" else (256, 22050, 80)
 
 
 def parse():
@@ -89,7 +97,7 @@ def workload_of(a):
 def describe(name, wl, world):
     """``config`` of the JSON line; identical in both arms so the driver can match them."""
     per = "in total, split over the ranks" if wl["scaling"] == "strong" else "per GPU"
-    hop, sr = (512, 44100) if wl["voc"] == "bigvgan_44k" else (256, 22050)
+    hop, sr, _ = voc_spec(wl["voc"])
     gen = wl["T"] - wl["Tp"]
     s = (f"{name}: {wl['model']} DiT (random init) + {wl['voc']}, {wl['steps']} Euler steps, cfg {wl['cfg']}, "
          f"{wl['B']} utterances {per} x T={wl['T']} frames (prompt {wl['Tp']}, generated {gen} = "
@@ -169,7 +177,9 @@ def _build_reference(wl):
     from seedvc_b200 import configs, synth
     import ref_import
 
-    h = configs.bigvgan_h(wl["voc"])
+    hop, sr, n_mels = voc_spec(wl["voc"])
+    h = configs.to_attr(dict(hop_size=hop, sampling_rate=sr, num_mels=n_mels)) if wl["voc"] == "hift" \
+        else configs.bigvgan_h(wl["voc"])
     if ref_import.available():
         ns = ref_import.load()
         from munch import Munch
@@ -195,14 +205,28 @@ def _build_reference(wl):
 
             def sampler(z, lens, prompt, mu, style, t_span):
                 return cfm.solve_euler(z, lens, prompt, mu, style, None, t_span, wl["cfg"])
-        voc = ns.BigVGAN(ns.BigVGANAttrDict(dict(h))).eval()
-        voc.remove_weight_norm()
+        if wl["voc"] == "hift":
+            import seedvc_oracle as orc
+            hk = {k: v for k, v in orc.HIFT_CFG.items() if k not in ("n_fft", "hop_len")}
+            hk["istft_params"] = {"n_fft": orc.HIFT_CFG["n_fft"], "hop_len": orc.HIFT_CFG["hop_len"]}
+            voc = ns.HiFTGenerator(**hk, f0_predictor=ns.ConvRNNF0Predictor(num_class=1, in_channels=80,
+                                                                            cond_channels=512)).eval()
+        else:
+            voc = ns.BigVGAN(ns.BigVGANAttrDict(dict(h))).eval()
+            voc.remove_weight_norm()
         synth.fill_parameters_(voc, seed=0)
         return ref_import.kind(), sampler, voc, dims, h
     # ---- fallback: the oracle port --------------------------------------------------------
     import seedvc_oracle as orc
     man = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
     sdv = synth.synth_state_dict(man["keys_" + wl["voc"]])
+    if wl["voc"] == "hift":
+        def port_voc(mel):
+            ph, nz = synth.synth_hift_noise(mel.shape[0], orc.HIFT_CFG["nb_harmonics"] + 1, mel.shape[-1] * 256)
+            return orc.hift_forward(sdv, mel, ph, nz)
+    else:
+        def port_voc(mel):
+            return orc.bigvgan_forward(sdv, h, mel)
     if wl["kind"] == "v2":
         kw = configs.v2_estimator_kwargs()
         sd = synth.synth_state_dict(man["keys_v2_small"])
@@ -217,7 +241,7 @@ def _build_reference(wl):
 
         def sampler(z, lens, prompt, mu, style, t_span):
             return orc.solve_euler_v1(sd, a, z, lens, prompt, mu, style, t_span, wl["cfg"])
-    return "port", sampler, (lambda mel: orc.bigvgan_forward(sdv, h, mel)), dims, h
+    return "port", sampler, port_voc, dims, h
 
 
 def cpu_sample(name, wl, threads):
@@ -261,8 +285,8 @@ def cpu_sample(name, wl, threads):
     what = {"reference": "the reference's own modules (/root/reference)",
             "oracle/_ref": "the reference's own modules (staged copy oracle/_ref)",
             "port": "oracle port (reference tree absent)"}[kind]
-    desc = (f"1 utterance of {name}: {n_s} of {N} Euler steps at T={T} (CFG stacked) through solve_euler + BigVGAN on "
-            f"{frames} of {gen} frames, scaled linearly to the full unit; {what}, fp32, {threads} threads")
+    desc = (f"1 utterance of {name}: {n_s} of {N} Euler steps at T={T} (CFG stacked) through solve_euler + the vocoder on "
+            f"{frames} of {gen} frames ({wl['voc']}), scaled linearly to the full unit; {what}, fp32, {threads} threads")
     return audio_s / total, kind, desc, t_s + t_v
 
 
@@ -339,8 +363,14 @@ def run_ours(a):
         cfm = CFM(args, mode=a.mode).to(dev)
         cfm.estimator.setup_caches(B, 8192)
         C, cd = args.DiT.in_channels, args.DiT.content_dim
-    voc = BigVGAN(configs.bigvgan_h(wl["voc"]), mode=a.mode).to(dev)
-    hop, sr = voc.h.hop_size, voc.h.sampling_rate
+    if wl["voc"] == "hift":
+        from seedvc_b200.hifigan import ConvRNNF0Predictor, HiFTGenerator
+        hift = HiFTGenerator(f0_predictor=ConvRNNF0Predictor(), mode=a.mode).to(dev)
+        voc = lambda mel: hift(mel).unsqueeze(1)            # (B, L) -> (B, 1, L) like BigVGAN
+        voc._prepare = hift._prepare
+    else:
+        voc = BigVGAN(configs.bigvgan_h(wl["voc"]), mode=a.mode).to(dev)
+    hop, sr, _ = voc_spec(wl["voc"])
     gen = T - Tp
 
     mu, prompt, style, z = synth.synth_batch(B, T, Tp, C, cd, first_id=first_utt)

@@ -137,7 +137,7 @@ int svc_norm_mod(const float* x, long long x_bstride, long long x_rstride, const
 int svc_norm_mod_copy(const float* x, long long x_bstride, long long x_rstride, const float* gamma,
                       const float* mul, const float* add, float eps, int mode, void* out, void* raw_out,
                       long long o_bstride, long long o_rstride, int B, int T, int D, int out_dtype,
-                      void* stream);
+                      int raw_dtype /* SVC_* of raw_out: out_dtype, or the other 16-bit format */, void* stream);
 
 /* ---------------------------------------------------------------------------
  * svc_snake_aa: anti-aliased Snake / SnakeBeta = 2x Kaiser-sinc FIR upsample, x + sin^2(a x)/b,
@@ -243,6 +243,179 @@ int svc_sola_stitch(const float* infer, long long infer_bstride, int infer_len, 
                     long long buf_bstride, const float* fade_in, const float* fade_out, float* out,
                     long long out_bstride, int* offsets, int B, int sola_buffer_frame, int sola_search_frame,
                     int block_frame, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * HiFT vocoder pieces (reference modules/hifigan/generator.py).  The generator's convolutions run on
+ * svc_gemm; these are the non-GEMM steps.
+ * ------------------------------------------------------------------------- */
+/* out = f(x) elementwise on a (B, T, C) fp32 view -> out_dtype view.  kind 0: leaky_relu(slope) (generator.py:404,424),
+ * 1: ELU (f0_predictor.py:33-49), 2: Snake x + sin^2(alpha_c x) / (alpha_c + 1e-9) (:79-90), 3: |x| (f0_predictor.py:55) */
+int svc_unary(const float* x, long long x_bstride, long long x_rstride, void* out, long long o_bstride,
+              long long o_rstride, int B, int T, int C, int kind, float slope, const float* alpha, int out_dtype,
+              int precise, void* stream);
+/* F0 (B, Tm) Hz -> harmonic source (B, Tm * scale): nn.Upsample(nearest) (:295,367), SineGen.forward (:208-243) with
+ * the phase draw `phase` (B, H) and the Gaussian draw `noise` (B, H, Tm * scale) or NULL given by the caller,
+ * tanh(Linear_{H -> 1}) (:270-275).  prefix_ws: B * H * Tm doubles of workspace. */
+int svc_hift_source(const float* f0, long long f0_bstride, const float* phase, const float* noise, const float* lin_w,
+                    float lin_b, double* prefix_ws, float* out, long long out_bstride, int B, int Tm, int H, int scale,
+                    float sampling_rate, float sine_amp, float noise_std, float voiced_threshold, void* stream);
+/* torch.stft(n_fft 16, hop 4, Hann, center, reflect) of s (B, L) (:372-378) -> (B, rows, Cpad) out_dtype with channels
+ * [re_0..re_8, im_0..im_8, 0...]; rows >= L / 4 + 1, rows past that are zero-filled. */
+int svc_hift_stft(const float* s, long long s_bstride, void* out, long long o_bstride, long long o_rstride, int B, int L,
+                  int rows, int Cpad, int out_dtype, void* stream);
+/* conv_post output x (B, TT, >= 18) fp32 -> waveform (B, 4 (TT - 1)): exp / sin heads, magnitude clip, polar,
+ * torch.istft(16, 4, Hann, center), clamp to +-audio_limit (:426-435, :380-385). */
+int svc_hift_istft(const float* x, long long x_bstride, long long x_rstride, float* wav, long long wav_bstride, int B,
+                   int TT, float clip_mag, float audio_limit, int precise, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Graph-level entry point: svc_dit_step = ONE estimator call (all CFG branches) of the Euler loop, i.e.
+ * DiT.forward from `cond_x_merge_linear` to the velocity (diffusion_transformer.py:508-537 with Transformer.forward
+ * :112-143, TransformerBlock :173-191, the WaveNet / final_mlp heads; v2: modules/v2/dit_wrapper.py:137-152,
+ * dit_model.py:109-143), built from the entry points above.  A host in any language prepares the two structs once
+ * per model / per solve and then calls svc_dit_step + svc_cfg_euler per Euler step; nothing is allocated inside.
+ *
+ * Layouts (all contiguous unless a stride is given; R = n_branch * B rows, Tq = T + ntok):
+ *   weights   (N, K) row-major in the dtype named; conv weights (k, N, K); w13 / WaveNet in-layers row-interleaved
+ *             for the pair activations (SVC_ACT_SWIGLU_PAIR / SVC_ACT_TANH_SIG_PAIR)
+ *   ada       per-step row of every AdaLN projection, fp32 (n_steps, n_ada): v1 chunks [w | b] (2D), v2 chunks
+ *             [shift, 1+scale, gate, shift, 1+scale, gate] (6D) per layer, final [mul | add], FinalLayer [shift | 1+scale]
+ *   h (R, Tq, D) fp32; xn, att (R, Tq, D), qkv (R, Tq, 3D), ff (R, Tq, I) op dtype; h_op, xn_f, skips (R, Tq, D),
+ *   x_res / y (R, T, D or Dw), xw_op (R, T + 2 pad, Dw), acts (R, T, wn_layers * Dw), ln (R, T, Dw) stream dtype;
+ *   xw, wn_out (R, T, Dw), v (R, T, C) fp32.
+ * ------------------------------------------------------------------------- */
+#define SVC_MAX_LAYERS 32
+#define SVC_MAX_WN_LAYERS 16
+#define SVC_MAX_BRANCH 3
+
+typedef struct svc_dit_weights {
+    int version;                       /* 1 (modules/diffusion_transformer.py) or 2 (modules/v2) */
+    int D, H, L, C, I;
+    int time_as_token, style_as_token, uvit, long_skip;
+    int head;                          /* 0 = final_mlp, 1 = WaveNet + FinalLayer + conv2 */
+    int Dw, wn_layers, wn_kernel;
+    int op_dtype, stream_dtype;        /* SVC_* of branch operands / of operands that carry the residual stream */
+    const void* wqkv[SVC_MAX_LAYERS];  /* op dtype */
+    const void* wo[SVC_MAX_LAYERS];
+    const void* w13[SVC_MAX_LAYERS];
+    const void* w2[SVC_MAX_LAYERS];
+    const float* g_attn[SVC_MAX_LAYERS];
+    const float* g_ffn[SVC_MAX_LAYERS];
+    const void* skip_w[SVC_MAX_LAYERS]; /* (D, 2D) stream dtype, NULL unless the layer receives a U-ViT skip */
+    const float* skip_b[SVC_MAX_LAYERS];
+    int ada_attn[SVC_MAX_LAYERS];      /* v1: offset of the attention-norm chunk in the ada row, -1 = plain RMSNorm; v2: offset of the 6D chunk */
+    int ada_ffn[SVC_MAX_LAYERS];       /* v1: offset of the ffn-norm chunk, -1 = plain RMSNorm */
+    const float* g_final;
+    int ada_final;
+    const void* merge_wx;              /* x columns of cond_x_merge_linear: (D, C) view, stream dtype */
+    long long merge_w_rstride;
+    const void* lskip_w;               /* skip_linear (D, D + C), stream dtype, or NULL */
+    const float* lskip_b;
+    const void* mlp0_w;                /* final_mlp (head 0), stream dtype */
+    const float* mlp0_b;
+    const void* mlp2_w;
+    const float* mlp2_b;
+    const void* conv1_w;               /* head 1, stream dtype */
+    const float* conv1_b;
+    const void* resp_w;
+    const void* conv2_w;
+    const float* conv2_b;
+    const void* fl_w;
+    const float* fl_b;
+    const void* wn_in_w[SVC_MAX_WN_LAYERS];   /* (k, 2 Dw, Dw) */
+    const void* wn_rs_w[SVC_MAX_WN_LAYERS];   /* res half of res_skip: (Dw, Dw) */
+    const float* wn_rs_b[SVC_MAX_WN_LAYERS];
+    const void* wn_skip_w;             /* (Dw, wn_layers * Dw): all skip halves side by side */
+    const float* wn_skip_b;            /* summed skip biases + res_projection bias */
+    int ada_fl;
+    const float* rope_tab;             /* (positions, 32, 2) */
+    const float* rope_tab_t;           /* pair-major copy (32, rope_ld, 2) */
+    int rope_ld;
+} svc_dit_weights;
+
+typedef struct svc_dit_state {
+    int B, T, n_branch, n_steps, n_ada;
+    const float* ada;                  /* (n_steps, n_ada) */
+    const float* t1;                   /* (n_steps, D): time token rows */
+    const float* wn_g;                 /* (n_steps, wn_layers * 2 Dw): WaveNet cond_layer output + in-layer bias */
+    int const_kind[SVC_MAX_BRANCH];    /* hoisted columns of cond_x_merge_linear: 0 = (B, T, D) fp32 matrix, 1 = D vector */
+    const float* const_ptr[SVC_MAX_BRANCH];
+    const float* style_tok;            /* (B, D) */
+    const float* style_tok_null;       /* (D) */
+    int branch_style[SVC_MAX_BRANCH];  /* 1: the branch sees the style token, 0: the null token */
+    const int* kv_len;                 /* (R) keys per row incl. tokens */
+    const int* wn_lens;                /* (R) frames per row */
+    float* h;
+    void* xn;
+    void* xn_f;
+    void* qkv;
+    void* att;
+    void* ff;
+    void* h_op;
+    void* skips[SVC_MAX_LAYERS / 2];
+    float* v;
+    void* x_res;
+    void* y;
+    float* xw;
+    void* xw_op;
+    void* acts;
+    float* wn_out;
+    void* ln;
+} svc_dit_state;
+
+/* velocity of every branch at Euler step s -> st->v (R, T, C) fp32.  x_op: (B, T, C) stream dtype (the copy
+ * svc_cfg_euler writes). */
+int svc_dit_step(const svc_dit_weights* w, const svc_dit_state* st, int s, const void* x_op, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Graph-level entry point: svc_bigvgan_forward = BigVGAN.forward (modules/bigvgan/bigvgan.py:360-386) with AMPBlock1
+ * (:132-141): conv_pre, per stage the polyphase ConvTranspose1d and 3 x 3 x [snake, conv, snake, conv, + x] with the
+ * (r0 + r1 + r2) / 3 average fused in the GEMM epilogues, activation_post + conv_post + clamp / tanh.  Weights are the
+ * prepared copies (folded weight-norm, (taps, N, K) conv layout, time-to-depth regrouping for the narrow stages,
+ * Snake exp(alpha) and 1 / (exp(beta) + 1e-9)).  The caller provides the workspace; nothing is allocated inside.
+ * ------------------------------------------------------------------------- */
+#define SVC_MAX_STAGES 8
+#define SVC_MAX_TAPS 16
+
+typedef struct svc_conv_plan {
+    int f;                             /* time-to-depth factor: the (B, L, O) buffer is read as (B, L / f, f * O) */
+    int n_taps;
+    int shifts[SVC_MAX_TAPS];          /* row shift of every tap (in regrouped rows) */
+    const void* w;                     /* (n_taps, f * O, f * I) operand dtype */
+    const float* b;                    /* (f * O) */
+    int k;                             /* kernel size of the original conv (FLOP accounting only) */
+} svc_conv_plan;
+
+typedef struct svc_amp_pair {
+    const float *a1, *inv_b1, *a2, *inv_b2;   /* Snake parameters of the two activations, (O) each */
+    svc_conv_plan c1, c2;
+} svc_amp_pair;
+
+typedef struct svc_bigvgan_stage {
+    int u, O;                          /* upsampling factor, output channels */
+    int n_delta;
+    int deltas[SVC_MAX_TAPS];
+    const void* up_w;                  /* (n_delta, u * O, I) polyphase weight */
+    const float* up_b;                 /* (u * O) */
+    svc_amp_pair pairs[3][3];          /* [resblock][dilation] */
+} svc_bigvgan_stage;
+
+typedef struct svc_bigvgan_weights {
+    int n_mels, c0, n_stages, n_kernels, n_dil;
+    int op_dtype, precise;
+    const void* pre_w;                 /* (7, c0, n_mels) */
+    const float* pre_b;
+    svc_bigvgan_stage stages[SVC_MAX_STAGES];
+    const float *post_a, *post_inv_b;
+    const float* post_w;               /* (post_k, C_last) fp32 */
+    const float* post_b;               /* or NULL */
+    int post_k, use_tanh;
+} svc_bigvgan_weights;
+
+long long svc_bigvgan_workspace_bytes(const svc_bigvgan_weights* w, int B, int Tm);
+/* mel (B, n_mels, Tm) fp32 -> out (B, Tm * prod(u)) fp32 in [-1, 1] */
+int svc_bigvgan_forward(const svc_bigvgan_weights* w, const float* mel, void* workspace, float* out, int B, int Tm,
+                        void* stream);
 
 #ifdef __cplusplus
 }

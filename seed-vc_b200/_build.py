@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libseedvc_b200.so")
-SOURCES = ["gemm.cu", "attention.cu", "elementwise.cu", "snake.cu"]
+SOURCES = ["gemm.cu", "attention.cu", "elementwise.cu", "snake.cu", "hift.cu", "graph.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",

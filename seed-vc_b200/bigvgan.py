@@ -108,6 +108,24 @@ def conv_plan(weight, bias, dilation, od, length_divisor_ok=True):
             "b": b.repeat(f).contiguous(), "k": k}
 
 
+def polyphase_plan(wt, u):
+    """ConvTranspose1d(I -> O, kernel k, stride u, padding (k - u) // 2) as a few-tap GEMM with N = u * O:
+        out[u*q + r] = sum_delta x[q + delta] . w[:, :, r + pad - u*delta].
+    wt: (I, O, k) folded weight.  Returns (deltas, poly (n_delta, u*O, I) fp32)."""
+    I, O, k = wt.shape
+    pad = (k - u) // 2
+    dmin = min(-((-(r + pad - k + 1)) // u) for r in range(u))   # ceil((r+pad-k+1)/u)
+    dmax = max((r + pad) // u for r in range(u))
+    deltas = list(range(dmin, dmax + 1))
+    poly = torch.zeros(len(deltas), u * O, I, device=wt.device)
+    for di, dl in enumerate(deltas):
+        for r in range(u):
+            kk = r + pad - u * dl
+            if 0 <= kk < k:
+                poly[di, r * O:(r + 1) * O, :] = wt[:, :, kk].t()
+    return deltas, poly
+
+
 class BigVGAN(nn.Module):
     def __init__(self, h, use_cuda_kernel: bool = False, mode: str = "bf16"):
         super().__init__()
@@ -210,18 +228,8 @@ class BigVGAN(nn.Module):
         stages = []
         for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
             wt = self.ups[i][0].weight.detach().float()          # (I, O, k)
-            I, O, _ = wt.shape
-            pad = (k - u) // 2
-            # polyphase: out[u*q + r] = sum_delta x[q + delta] . w[:, :, r + pad - u*delta]
-            dmin = min(-((-(r + pad - k + 1)) // u) for r in range(u))   # ceil((r+pad-k+1)/u)
-            dmax = max((r + pad) // u for r in range(u))
-            deltas = list(range(dmin, dmax + 1))
-            poly = torch.zeros(len(deltas), u * O, I, device=wt.device)
-            for di, dl in enumerate(deltas):
-                for r in range(u):
-                    kk = r + pad - u * dl
-                    if 0 <= kk < k:
-                        poly[di, r * O:(r + 1) * O, :] = wt[:, :, kk].t()
+            O = wt.shape[1]
+            deltas, poly = polyphase_plan(wt, u)
             st = {"u": u, "O": O, "deltas": deltas, "up_w": poly.to(od).contiguous(),
                   "up_b": f32(self.ups[i][0].bias).repeat(u).contiguous(), "blocks": []}
             for j in range(self.num_kernels):
@@ -240,7 +248,49 @@ class BigVGAN(nn.Module):
         w["post_a"] = snake(self.activation_post)
         w["post_w"] = f32(self.conv_post.weight[0].t())           # (k, C)
         w["post_b"] = f32(self.conv_post.bias) if self.use_bias_at_final else None
+        w["c"] = self._c_weights(w, ops) if hasattr(ops, "bigvgan_forward") else None
         return w
+
+    def _c_weights(self, w, ops):
+        """svc_bigvgan_weights over the prepared tensors (kept alive by ``w``)."""
+        from . import _lib
+        c = _lib.BigVGANWeights()
+        h = self.h
+        c.n_mels, c.c0, c.n_stages = h.num_mels, h.upsample_initial_channel, len(w["stages"])
+        c.n_kernels, c.n_dil = self.num_kernels, len(h.resblock_dilation_sizes[0])
+        if any(len(d) != c.n_dil for d in h.resblock_dilation_sizes) or c.n_kernels > 3 or c.n_dil > 3:
+            return None                                        # shapes outside the C struct: Python sequence
+        c.op_dtype, c.precise = ops.op_code, ops.precise
+        c.pre_w, c.pre_b = w["pre_w"].data_ptr(), w["pre_b"].data_ptr()
+
+        def plan(dst, p):
+            dst.f, dst.n_taps, dst.k = p["f"], len(p["shifts"]), p["k"]
+            for i, sh in enumerate(p["shifts"]):
+                dst.shifts[i] = sh
+            dst.w, dst.b = p["w"].data_ptr(), p["b"].data_ptr()
+
+        for si, st in enumerate(w["stages"]):
+            cs = c.stages[si]
+            cs.u, cs.O, cs.n_delta = st["u"], st["O"], len(st["deltas"])
+            for i, d in enumerate(st["deltas"]):
+                cs.deltas[i] = d
+            cs.up_w, cs.up_b = st["up_w"].data_ptr(), st["up_b"].data_ptr()
+            for j, pairs in enumerate(st["blocks"]):
+                for l, pr in enumerate(pairs):
+                    cp = cs.pairs[j][l]
+                    cp.a1, cp.inv_b1 = pr["a1"][0].data_ptr(), pr["a1"][1].data_ptr()
+                    cp.a2, cp.inv_b2 = pr["a2"][0].data_ptr(), pr["a2"][1].data_ptr()
+                    plan(cp.c1, pr["c1"])
+                    plan(cp.c2, pr["c2"])
+        c.post_a, c.post_inv_b = w["post_a"][0].data_ptr(), w["post_a"][1].data_ptr()
+        c.post_w, c.post_k = w["post_w"].data_ptr(), w["post_w"].shape[0]
+        c.post_b = w["post_b"].data_ptr() if w["post_b"] is not None else None
+        c.use_tanh = int(bool(self.use_tanh_at_final))
+        return c
+
+    def launches_per_call(self):
+        n_st = len(self.h.upsample_rates)
+        return 2 + n_st * (1 + self.num_kernels * len(self.h.resblock_dilation_sizes[0]) * 4) + 1
 
     @torch.no_grad()
     def forward(self, x):
@@ -250,6 +300,15 @@ class BigVGAN(nn.Module):
         dev = x.device
         B, n_mels, Tm = x.shape
         f32 = torch.float32
+        if w.get("c") is not None and ops.profile is None:
+            # ONE call of the graph-level C entry point (csrc/graph.cu) issues the launch sequence written out below
+            mel = x.float().contiguous()
+            up = 1
+            for u in self.h.upsample_rates:
+                up *= u
+            out = torch.empty(B, Tm * up, dtype=f32, device=dev)
+            ops.bigvgan_forward(w["c"], mel, out, B, Tm, self.launches_per_call())
+            return out.view(B, 1, Tm * up)
         mel_op = ops.empty(B, Tm, n_mels, device=dev)
         ops.bct_to_btc(x.float().contiguous(), mel_op)
         c0 = self.h.upsample_initial_channel

@@ -91,6 +91,13 @@ __device__ __forceinline__ float2 poly_exp2_x2(float2 x) {
     return r;
 }
 
+// 3-input max (FMNMX3, sm_100+): halves the instruction count of a row-max pass
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 template <int N>
 __device__ __forceinline__ void reg_dealloc() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
@@ -132,6 +139,11 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 // pipe (8 cycles per warp instruction per SM sub-partition, measured: scripts/ubench/mufu.cu)
 // and by the fixed latencies of a block (barrier round trips, tcgen05.ld/st); three free-running
 // groups per SM keep that pipe ~70% busy, where two groups taking turns reached 60%.
+// Measured dead ends (round 2, B = 64, T = 2580, H = 8, isolated): skipping the per-block row max after block 0
+// ("lazy max", guarded by the block sum) ran at 666 TFLOP/s against 872 with the FMNMX3 row max kept - the extra
+// control dependency costs more than the 72 instructions it removes; polynomial exp2 on every 2nd / 4th pair
+// 585 / 681 (every 3rd stays best); the packed ex2.approx.bf16x2 / f16x2 forms compile to two MUFU.EX2
+// instructions per pair (scripts/ubench/mufu2.cu), so they cannot lift the XU bound either.
 // F16: operands (Q, K, V, the P tile and the output) are IEEE half instead of bf16 - same instruction, the
 // format bits of the instruction descriptor and the conversions differ.
 template <bool F16>
@@ -334,7 +346,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
                         if (TAIL && kbase + c * 32 + i >= kv_len) s[c][i] = -INFINITY;
                     }
             }
-            // row max with 8 independent chains (a single fmax chain is AT_BN x 4 cycles of latency)
+            // row max: 8 independent chains of 3-input max (a single fmax chain is AT_BN x 4 cycles of latency)
             auto rowmax = [&]() {
                 float mxa[8];
 #pragma unroll
@@ -342,9 +354,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attention_tc_kernel(const __gri
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mxa[i & 7] = fmaxf(mxa[i & 7], s[c][i]);
-                return kLog2e * fmaxf(fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])),
-                                      fmaxf(fmaxf(mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7])));
+                    for (int i = 0; i < 32; i += 2) mxa[(i >> 1) & 7] = fmax3(mxa[(i >> 1) & 7], s[c][i], s[c][i + 1]);
+                return kLog2e * fmax3(fmax3(mxa[0], mxa[1], mxa[2]), fmax3(mxa[3], mxa[4], mxa[5]), fmaxf(mxa[6], mxa[7]));
             };
             // p = 2^(s * log2e - m) for the block, packed to bf16 pairs; returns the row sum.
             // Packed f32x2 arithmetic: one FFMA2 / FADD2 per pair of keys.

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) norm_mod_kernel(
     const float* __restrict__ x, long long x_bstride, long long x_rstride,
     const float* __restrict__ gamma, const float* __restrict__ mul, const float* __restrict__ add,
     float eps, int mode, TO* __restrict__ out, long long o_bstride, long long o_rstride, int B, int T,
-    int D, TO* __restrict__ raw) {
+    int D, TO* __restrict__ raw, int raw_f16) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= B * T) return;
@@ -87,9 +87,9 @@ __global__ void __launch_bounds__(256) norm_mod_kernel(
                 if constexpr (sizeof(TO) == 4) {
                     *reinterpret_cast<float4*>(rrow + c) = v[i];
                 } else {
-                    uint2 q;
-                    q.x = pack2<TO>(v[i].x, v[i].y);
-                    q.y = pack2<TO>(v[i].z, v[i].w);
+                    uint2 q;             // the raw copy may use the other 16-bit format than the normalised output
+                    q.x = pack_op16_rt(v[i].x, v[i].y, raw_f16);
+                    q.y = pack_op16_rt(v[i].z, v[i].w, raw_f16);
                     *reinterpret_cast<uint2*>(rrow + c) = q;
                 }
             }
@@ -251,7 +251,7 @@ using namespace svc;
 static int norm_mod_impl(const float* x, long long x_bstride, long long x_rstride,
                             const float* gamma, const float* mul, const float* add, float eps,
                             int mode, void* out, long long o_bstride, long long o_rstride, int B,
-                            int T, int D, int out_dtype, void* stream, void* raw_out) {
+                            int T, int D, int out_dtype, void* stream, void* raw_out, int raw_dtype) {
     if (D % 4 != 0 || D > 2048 || B < 1 || T < 1) {
         svc_set_error("svc_norm_mod: D must be a multiple of 4 and <= 2048");
         return SVC_ERR_ARG;
@@ -274,7 +274,7 @@ static int norm_mod_impl(const float* x, long long x_bstride, long long x_rstrid
     norm_mod_kernel<TO, MAXV><<<blocks, 256, 0, st>>>(x, x_bstride, x_rstride, gamma, mul, add, \
                                                       eps, mode, static_cast<TO*>(out),         \
                                                       o_bstride, o_rstride, B, T, D,             \
-                                                      static_cast<TO*>(raw_out))
+                                                      static_cast<TO*>(raw_out), raw_dtype == SVC_F16)
     if (out_dtype == SVC_F32) {
         if (D <= 512) LAUNCH_NORM(float, 4);
         else if (D <= 1024) LAUNCH_NORM(float, 8);
@@ -298,15 +298,19 @@ extern "C" int svc_norm_mod(const float* x, long long x_bstride, long long x_rst
                             long long o_bstride, long long o_rstride, int B, int T, int D, int out_dtype,
                             void* stream) {
     return norm_mod_impl(x, x_bstride, x_rstride, gamma, mul, add, eps, mode, out, o_bstride, o_rstride, B, T, D,
-                         out_dtype, stream, nullptr);
+                         out_dtype, stream, nullptr, out_dtype);
 }
 
 extern "C" int svc_norm_mod_copy(const float* x, long long x_bstride, long long x_rstride, const float* gamma,
                                  const float* mul, const float* add, float eps, int mode, void* out,
                                  void* raw_out, long long o_bstride, long long o_rstride, int B, int T, int D,
-                                 int out_dtype, void* stream) {
+                                 int out_dtype, int raw_dtype, void* stream) {
+    if ((out_dtype == SVC_F32) != (raw_dtype == SVC_F32)) {
+        svc_set_error("svc_norm_mod_copy: raw_dtype must be out_dtype or the other 16-bit format");
+        return SVC_ERR_ARG;
+    }
     return norm_mod_impl(x, x_bstride, x_rstride, gamma, mul, add, eps, mode, out, o_bstride, o_rstride, B, T, D,
-                         out_dtype, stream, raw_out);
+                         out_dtype, stream, raw_out, raw_dtype);
 }
 
 extern "C" int svc_cfg_euler(float* x, const float* v, int n_branch, float c0, float c1, float c2,

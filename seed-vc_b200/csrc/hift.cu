@@ -9,6 +9,8 @@
 // element (or frame), coalesced along the contiguous axis.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace svc {
@@ -19,28 +21,52 @@ __device__ __forceinline__ void store_elem(TO* p, float v) {
 }
 
 // ------------------------------------------------------------------------------------------ unary
-template <typename TO, bool PRECISE>
+template <bool PRECISE>
+__device__ __forceinline__ float unary_fn(float v, int kind, float slope, float a) {
+    if (kind == 0) return v > 0.f ? v : v * slope;                                   // F.leaky_relu
+    if (kind == 1) return v > 0.f ? v : (PRECISE ? expm1f(v) : __expf(v) - 1.0f);    // nn.ELU(alpha = 1)
+    if (kind == 2) {                                                                 // Snake, linear-scale alpha (:79-90)
+        const float s = PRECISE ? sinf(v * a) : __sinf(v * a);
+        return v + (1.0f / (a + 1e-9f)) * s * s;
+    }
+    return fabsf(v);
+}
+
+// grid (row blocks, B): a block walks rows t = blockIdx.x, + gridDim.x, ...; threads cover the row 4 channels at a
+// time (float4 in, 8 / 16-byte packed out), so every access is a contiguous row segment and nothing is divided.
+template <typename TO, bool PRECISE, bool VEC>
 __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ x, long long xbs, long long xrs,
                                                     TO* __restrict__ out, long long obs, long long ors, int T, int C,
                                                     int kind, float slope, const float* __restrict__ alpha) {
     const int b = blockIdx.y;
-    const long long n = static_cast<long long>(T) * C;
-    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
-        const int t = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<long long>(t) * C);
-        const float v = x[b * xbs + t * xrs + c];
-        float y;
-        if (kind == 0) {
-            y = v > 0.f ? v : v * slope;                                  // F.leaky_relu
-        } else if (kind == 1) {
-            y = v > 0.f ? v : (PRECISE ? expm1f(v) : __expf(v) - 1.0f);   // nn.ELU(alpha = 1)
-        } else if (kind == 2) {                                           // Snake, linear-scale alpha (:79-90)
-            const float a = __ldg(alpha + c);
-            const float s = PRECISE ? sinf(v * a) : __sinf(v * a);
-            y = v + (1.0f / (a + 1e-9f)) * s * s;
-        } else {
-            y = fabsf(v);
+    const int lanes = VEC ? C / 4 : C;                // work items per row
+    const int rows_per_pass = 256 / lanes > 0 ? 256 / lanes : 1;
+    const int sub = threadIdx.x / lanes, li = threadIdx.x % lanes;
+    for (int t0 = blockIdx.x * rows_per_pass; t0 < T; t0 += gridDim.x * rows_per_pass) {
+        const int t = t0 + sub;
+        if (sub >= rows_per_pass || t >= T) continue;
+        for (int i = li; i < lanes; i += (lanes < 256 ? lanes : 256)) {
+            if constexpr (VEC) {
+                const int c = 4 * i;
+                const float4 v = *reinterpret_cast<const float4*>(x + b * xbs + t * xrs + c);
+                float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (kind == 2) a4 = __ldg(reinterpret_cast<const float4*>(alpha + c));
+                const float y0 = unary_fn<PRECISE>(v.x, kind, slope, a4.x), y1 = unary_fn<PRECISE>(v.y, kind, slope, a4.y);
+                const float y2 = unary_fn<PRECISE>(v.z, kind, slope, a4.z), y3 = unary_fn<PRECISE>(v.w, kind, slope, a4.w);
+                TO* o = out + b * obs + t * ors + c;
+                if constexpr (sizeof(TO) == 4) {
+                    *reinterpret_cast<float4*>(o) = make_float4(y0, y1, y2, y3);
+                } else {
+                    uint2 q;
+                    q.x = pack2<TO>(y0, y1);
+                    q.y = pack2<TO>(y2, y3);
+                    *reinterpret_cast<uint2*>(o) = q;
+                }
+            } else {
+                const float v = x[b * xbs + t * xrs + i];
+                store_elem<TO>(out + b * obs + t * ors + i, unary_fn<PRECISE>(v, kind, slope, kind == 2 ? __ldg(alpha + i) : 0.f));
+            }
         }
-        store_elem<TO>(out + b * obs + t * ors + c, y);
     }
 }
 
@@ -218,16 +244,21 @@ extern "C" int svc_unary(const float* x, long long x_bstride, long long x_rstrid
         return SVC_ERR_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const long long n = static_cast<long long>(T) * C;
-    dim3 grid(static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148LL * 32)), B);
-#define UNARY(TO)                                                                                                  \
-    do {                                                                                                           \
-        if (precise)                                                                                               \
-            unary_kernel<TO, true><<<grid, 256, 0, st>>>(x, x_bstride, x_rstride, static_cast<TO*>(out), o_bstride,  \
-                                                         o_rstride, T, C, kind, slope, alpha);                     \
-        else                                                                                                       \
-            unary_kernel<TO, false><<<grid, 256, 0, st>>>(x, x_bstride, x_rstride, static_cast<TO*>(out), o_bstride, \
-                                                          o_rstride, T, C, kind, slope, alpha);                    \
+    const int esz = out_dtype == SVC_F32 ? 4 : 2;
+    const bool vec = C % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && x_bstride % 4 == 0 && x_rstride % 4 == 0 &&
+                     reinterpret_cast<uintptr_t>(out) % 16 == 0 && (o_bstride * esz) % 16 == 0 &&
+                     (o_rstride * esz) % (esz == 4 ? 16 : 8) == 0 &&
+                     (alpha == nullptr || reinterpret_cast<uintptr_t>(alpha) % 16 == 0);
+    const int lanes = vec ? C / 4 : C;
+    const int rows_per_pass = lanes >= 256 ? 1 : 256 / lanes;
+    dim3 grid(static_cast<unsigned>(std::min<long long>((T + rows_per_pass - 1) / rows_per_pass, 148LL * 16)), B);
+#define UNARY_V(TO, P, V)                                                                                          \
+    unary_kernel<TO, P, V><<<grid, 256, 0, st>>>(x, x_bstride, x_rstride, static_cast<TO*>(out), o_bstride, o_rstride, \
+                                                 T, C, kind, slope, alpha)
+#define UNARY(TO)                                                  \
+    do {                                                           \
+        if (precise) { if (vec) UNARY_V(TO, true, true); else UNARY_V(TO, true, false); }    \
+        else { if (vec) UNARY_V(TO, false, true); else UNARY_V(TO, false, false); }          \
     } while (0)
     if (out_dtype == SVC_F32) UNARY(float);
     else if (out_dtype == SVC_F16) UNARY(__half);
@@ -237,6 +268,7 @@ extern "C" int svc_unary(const float* x, long long x_bstride, long long x_rstrid
         return SVC_ERR_ARG;
     }
 #undef UNARY
+#undef UNARY_V
     SVC_CHECK_LAUNCH();
     return SVC_OK;
 }

@@ -20,6 +20,11 @@ __constant__ float c_h12[12] = {
     0.0020289648f, 0.0093894657f, -0.0255434588f, -0.0576573834f, 0.1285725832f, 0.4432097971f,
     0.4432097971f, 0.1285725832f, -0.0576573834f, -0.0255434588f, 0.0093894657f, 0.0020289648f};
 
+// the same taps doubled: the upsampler's gain of 2 (resample.py:36) folded into the FIR (exact: a power of two)
+__constant__ float c_h12x2[12] = {
+    2 * 0.0020289648f, 2 * 0.0093894657f, 2 * -0.0255434588f, 2 * -0.0576573834f, 2 * 0.1285725832f, 2 * 0.4432097971f,
+    2 * 0.4432097971f, 2 * 0.1285725832f, 2 * -0.0576573834f, 2 * -0.0255434588f, 2 * 0.0093894657f, 2 * 0.0020289648f};
+
 template <bool PRECISE>
 __device__ __forceinline__ float snake_fn(float u, float a, float inv_b) {
     const float s = PRECISE ? sinf(u * a) : __sinf(u * a);
@@ -215,11 +220,11 @@ __global__ void __launch_bounds__(256) snake_aa2_kernel(const TI* __restrict__ x
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
                 const float2 xv = ld(r0 + pz - j);
-                e = __ffma2_rn(splat2(c_h12[2 * j]), xv, e);
-                o = __ffma2_rn(splat2(c_h12[2 * j + 1]), xv, o);
+                e = __ffma2_rn(splat2(c_h12x2[2 * j]), xv, e);
+                o = __ffma2_rn(splat2(c_h12x2[2 * j + 1]), xv, o);
             }
-            uw[2 * pz] = snake_fn2<PRECISE>(__fmul2_rn(e, splat2(2.0f)), a, inv_b);
-            uw[2 * pz + 1] = snake_fn2<PRECISE>(__fmul2_rn(o, splat2(2.0f)), a, inv_b);
+            uw[2 * pz] = snake_fn2<PRECISE>(e, a, inv_b);
+            uw[2 * pz + 1] = snake_fn2<PRECISE>(o, a, inv_b);
         }
 #pragma unroll
         for (int j = 0; j < 5; ++j) xw[j + 1] = ld(r0 + j);
@@ -231,11 +236,11 @@ __global__ void __launch_bounds__(256) snake_aa2_kernel(const TI* __restrict__ x
             float2 e = splat2(0.f), o = splat2(0.f);
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                e = __ffma2_rn(splat2(c_h12[2 * j]), xw[5 - j], e);
-                o = __ffma2_rn(splat2(c_h12[2 * j + 1]), xw[5 - j], o);
+                e = __ffma2_rn(splat2(c_h12x2[2 * j]), xw[5 - j], e);
+                o = __ffma2_rn(splat2(c_h12x2[2 * j + 1]), xw[5 - j], o);
             }
-            uw[10] = snake_fn2<PRECISE>(__fmul2_rn(e, splat2(2.0f)), a, inv_b);
-            uw[11] = snake_fn2<PRECISE>(__fmul2_rn(o, splat2(2.0f)), a, inv_b);
+            uw[10] = snake_fn2<PRECISE>(e, a, inv_b);
+            uw[11] = snake_fn2<PRECISE>(o, a, inv_b);
             float2 y = splat2(0.f);
 #pragma unroll
             for (int k = 0; k < 12; ++k) y = __ffma2_rn(splat2(c_h12[k]), uw[k], y);

@@ -98,6 +98,7 @@ class DiTEngine:
     # ------------------------------------------------------------------ weights
     def load_weights(self, sd, device):
         """Fold weight-norm, fuse / interleave / split and cast the reference state_dict."""
+        self._cw = None
         sp, ops = self.spec, self.ops
         p = sp.prefix
         od = ops.op_dtype
@@ -245,7 +246,77 @@ class DiTEngine:
     def setup_rope(self, n_pos, device):
         if self.rope is None or self.max_pos < n_pos:
             self.rope = rope_table(n_pos, bf16_round=self.spec.version == 2).to(device)
+            self.rope_t = self.rope.permute(1, 0, 2).contiguous()      # pair-major copy for the row-layout epilogue
             self.max_pos = n_pos
+            self._cw = None
+
+    # ------------------------------------------------------------------ C structs of svc_dit_step
+    def _c_weights(self):
+        """svc_dit_weights over the prepared tensors (kept alive by self.w)."""
+        if getattr(self, "_cw", None) is not None:
+            return self._cw
+        from . import _lib
+        sp, w, ops = self.spec, self.w, self.ops
+        c = _lib.DitWeights()
+        c.version, c.D, c.H, c.L, c.C, c.I = sp.version, sp.D, sp.H, sp.L, sp.C, sp.I
+        c.time_as_token, c.style_as_token = int(sp.time_as_token), int(sp.style_as_token)
+        c.uvit, c.long_skip = int(sp.uvit), int(sp.long_skip)
+        c.head = 1 if sp.head == "wavenet" else 0
+        c.Dw, c.wn_layers, c.wn_kernel = sp.Dw, sp.wn_layers, sp.wn_kernel
+        c.op_dtype, c.stream_dtype = ops._code(ops.op_dtype), ops._code(ops.stream_dtype)
+        idx = w["ada_index"]
+        for i, lw in enumerate(w["layers"]):
+            c.wqkv[i], c.wo[i], c.w13[i], c.w2[i] = (lw[k].data_ptr() for k in ("wqkv", "wo", "w13", "w2"))
+            c.g_attn[i], c.g_ffn[i] = lw["g_attn"].data_ptr(), lw["g_ffn"].data_ptr()
+            if "skip_w" in lw:
+                c.skip_w[i], c.skip_b[i] = lw["skip_w"].data_ptr(), lw["skip_b"].data_ptr()
+            if sp.version == 1:
+                c.ada_attn[i] = idx[f"attn{i}"][0] if f"attn{i}" in idx else -1
+                c.ada_ffn[i] = idx[f"ffn{i}"][0] if f"ffn{i}" in idx else -1
+            else:
+                c.ada_attn[i], c.ada_ffn[i] = idx[f"blk{i}"][0], -1
+        c.g_final, c.ada_final = w["g_final"].data_ptr(), idx["final"][0]
+        c.merge_wx, c.merge_w_rstride = w["merge_w"].data_ptr(), w["merge_w"].stride(0)
+        if sp.long_skip:
+            c.lskip_w, c.lskip_b = w["lskip_w"].data_ptr(), w["lskip_b"].data_ptr()
+        if sp.head == "mlp":
+            c.mlp0_w, c.mlp0_b = w["mlp0_w"].data_ptr(), w["mlp0_b"].data_ptr()
+            c.mlp2_w, c.mlp2_b = w["mlp2_w"].data_ptr(), w["mlp2_b"].data_ptr()
+        else:
+            c.conv1_w, c.conv1_b, c.resp_w = w["conv1_w"].data_ptr(), w["conv1_b"].data_ptr(), w["resp_w"].data_ptr()
+            c.conv2_w, c.conv2_b = w["conv2_w"].data_ptr(), w["conv2_b"].data_ptr()
+            c.fl_w, c.fl_b = w["fl_w"].data_ptr(), w["fl_b"].data_ptr()
+            for l, wl in enumerate(w["wn"]):
+                c.wn_in_w[l], c.wn_rs_w[l] = wl["in_w"].data_ptr(), wl["rs_w"].data_ptr()
+                c.wn_rs_b[l] = wl["rs_b_res"].data_ptr()
+            c.wn_skip_w, c.wn_skip_b = w["wn_skip_w"].data_ptr(), w["wn_skip_b"].data_ptr()
+            c.ada_fl = idx["fl"][0]
+        c.rope_tab, c.rope_tab_t, c.rope_ld = self.rope.data_ptr(), self.rope_t.data_ptr(), self.rope.shape[0]
+        self._cw = c
+        return c
+
+    def _c_state(self, st):
+        from . import _lib
+        sp = self.spec
+        c = _lib.DitState()
+        c.B, c.T, c.n_branch, c.n_steps, c.n_ada = st["B"], st["T"], st["nb"], st["N"], st["ada"].shape[1]
+        c.ada, c.t1 = st["ada"].data_ptr(), st["t1"].data_ptr()
+        if "wn_g" in st:
+            c.wn_g = st["wn_g"].data_ptr()
+        for k, (kind, val) in enumerate(st["consts"]):
+            c.const_kind[k], c.const_ptr[k] = (0 if kind == "mat" else 1), val.data_ptr()
+        if sp.style_as_token:
+            c.style_tok, c.style_tok_null = st["style_tok"].data_ptr(), st["style_tok_null"].data_ptr()
+            for k, (use_p, use_s, use_m) in enumerate(st["branches"]):
+                c.branch_style[k] = int(bool(use_s))
+        c.kv_len = st["kv_len"].data_ptr()
+        for name in ("h", "xn", "xn_f", "qkv", "att", "ff", "h_op", "v", "x_res", "y", "xw", "xw_op", "acts",
+                     "wn_out", "ln", "wn_lens"):
+            if name in st:
+                setattr(c, name, st[name].data_ptr())
+        for k, t in enumerate(st["skips"]):
+            c.skips[k] = t.data_ptr()
+        return c
 
     # ------------------------------------------------------------------ per-solve precompute
     def begin(self, branches, prompt_op, mu, style, x_lens, t_values):
@@ -392,7 +463,18 @@ class DiTEngine:
             st["y"] = torch.empty(R, T, Dw, dtype=sdt, device=dev)
             st["wn_lens"] = st["x_lens"].repeat(nb).contiguous()
         self.st = st
+        st["c_state"] = self._c_state(st) if hasattr(ops, "dit_step") else None
         return st
+
+    def launches_per_step(self):
+        """Kernel launches of one estimator call (for the gpu_launches bookkeeping of the C path)."""
+        sp, st = self.spec, self.st
+        nb, L = st["nb"], sp.L
+        n = nb + int(sp.time_as_token) + (nb if sp.style_as_token else 0)
+        n += L * 7 + (L - L // 2 - 1 if sp.uvit else 0) + 1
+        n += nb if sp.long_skip else 0
+        n += 2 if sp.head == "mlp" else (2 + sp.wn_layers + 2 * (sp.wn_layers - 1) + 1 + 3)
+        return n
 
     # ------------------------------------------------------------------ one estimator call
     def _ada(self, s, name):
@@ -400,7 +482,15 @@ class DiTEngine:
         return self.st["ada"][s, lo:lo + n]
 
     def step(self, s, x_op):
-        """Velocity of every branch at step ``s``: (nb*B, T, C) fp32.  x_op: (B, T, C)."""
+        """Velocity of every branch at step ``s``: (nb*B, T, C) fp32.  x_op: (B, T, C).
+
+        On the CUDA library this is ONE call of the graph-level C entry point ``svc_dit_step`` (csrc/graph.cu),
+        which issues exactly the launch sequence written out below; the Python sequence runs when per-launch
+        profiling is on (bench.py's kernel breakdown) and on the emulated ops of the CPU host-logic tests."""
+        if self.st.get("c_state") is not None and self.ops.profile is None:
+            assert x_op.is_contiguous() and x_op.dtype == self.ops.stream_dtype
+            self.ops.dit_step(self._c_weights(), self.st["c_state"], s, x_op, self.launches_per_step())
+            return self.st["v"]
         sp, ops, w, st = self.spec, self.ops, self.w, self.st
         B, T, Tq, nb = st["B"], st["T"], st["Tq"], st["nb"]
         D, C, L, H = sp.D, sp.C, sp.L, sp.H
@@ -466,8 +556,7 @@ class DiTEngine:
                 ops.norm_mod(h, xn, gamma=lw["g_ffn"], mul=a[4 * D:5 * D], add=a[3 * D:4 * D])
             ops.gemm([(xn, 0, lw["w13"])], 2 * sp.I, B=R, T=Tq, act=ACT_SWIGLU_PAIR, out_op=ff)
             out_op = None
-            if i in emit and sp.version == 1 and (i + 1) < L and (i + 1) not in recv and \
-                    ops.stream_dtype == ops.op_dtype:
+            if i in emit and sp.version == 1 and (i + 1) < L and (i + 1) not in recv:
                 pending_raw = skip_bufs.pop(0)       # filled by layer i+1's attention norm
                 skips.append(pending_raw)
             elif i in emit:

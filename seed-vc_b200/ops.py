@@ -174,6 +174,25 @@ class Ops:
         check(self.lib.svc_gemm(C.byref(d), self.backend, self._stream()), "svc_gemm")
         self._t1()
 
+    # ------------------------------------------------------------------ graph-level estimator call
+    def dit_step(self, c_weights, c_state, s, x_op, n_launches):
+        """svc_dit_step: every kernel of one estimator call, sequenced on the C side (csrc/graph.cu)."""
+        self.launches += n_launches
+        check(self.lib.svc_dit_step(C.byref(c_weights), C.byref(c_state), int(s), x_op.data_ptr(), self._stream()),
+              "svc_dit_step")
+
+    def bigvgan_forward(self, c_weights, mel, out, B, Tm, n_launches):
+        """svc_bigvgan_forward: the whole vocoder, sequenced on the C side; the workspace comes from torch's
+        caching allocator."""
+        self._chk(mel, out)
+        n = int(self.lib.svc_bigvgan_workspace_bytes(C.byref(c_weights), B, Tm))
+        if n <= 0:
+            raise _lib.SvcError("svc_bigvgan_workspace_bytes failed")
+        ws = torch.empty(n, dtype=torch.uint8, device=mel.device)
+        self.launches += n_launches
+        check(self.lib.svc_bigvgan_forward(C.byref(c_weights), mel.data_ptr(), ws.data_ptr(), out.data_ptr(), B, Tm,
+                                           self._stream()), "svc_bigvgan_forward")
+
     # ------------------------------------------------------------------ attention
     def attention(self, qkv, out, H, kv_len):
         """qkv: (B, T, 3*H*64) packed [q|k|v] (RoPE + scale applied); out: (B, T, H*64)."""
@@ -209,11 +228,12 @@ class Ops:
                                         out.stride(1), B, T, D, self._code(out.dtype), self._stream()),
                   "svc_norm_mod")
         else:
-            assert raw_out.shape == out.shape and raw_out.dtype == out.dtype and raw_out.stride() == out.stride()
+            assert raw_out.shape == out.shape and raw_out.stride() == out.stride()
+            assert raw_out.element_size() == out.element_size()      # same layout; the 16-bit format may differ
             check(self.lib.svc_norm_mod_copy(x.data_ptr(), x.stride(0), x.stride(1), _ptr(gamma), _ptr(mul),
                                              _ptr(add), float(eps), mode, out.data_ptr(), raw_out.data_ptr(),
                                              out.stride(0), out.stride(1), B, T, D, self._code(out.dtype),
-                                             self._stream()), "svc_norm_mod_copy")
+                                             self._code(raw_out.dtype), self._stream()), "svc_norm_mod_copy")
         self._t1()
 
     # ------------------------------------------------------------------ BigVGAN activations
@@ -423,3 +443,57 @@ class Ops:
         check(self.lib.svc_log_clamp(x.data_ptr(), x.numel(), clip, self._stream()), "svc_log_clamp")
         self._t1()
 
+
+    # ------------------------------------------------------------------ HiFT vocoder pieces
+    UNARY_LRELU, UNARY_ELU, UNARY_SNAKE, UNARY_ABS = 0, 1, 2, 3
+
+    def unary(self, x, out, kind, slope=0.0, alpha=None):
+        """out = f(x) on (B, T, C) fp32 -> out's dtype; see svc_unary."""
+        self._chk(x, out, alpha)
+        B, T, Cc = x.shape
+        assert x.dtype == torch.float32 and x.stride(2) == 1 and out.shape == x.shape and out.stride(2) == 1
+        self._t0("hift_unary", 0.0, float(B) * T * Cc * (4 + out.element_size()))
+        check(self.lib.svc_unary(x.data_ptr(), x.stride(0), x.stride(1), out.data_ptr(), out.stride(0), out.stride(1),
+                                 B, T, Cc, kind, float(slope), _ptr(alpha), self._code(out.dtype), self.precise,
+                                 self._stream()), "svc_unary")
+        self._t1()
+
+    def hift_source(self, f0, phase, noise, lin_w, lin_b, out, scale, sr, sine_amp, noise_std, voiced_thr):
+        """f0 (B, Tm) fp32, phase (B, H), noise (B, H, Tm*scale) or None -> out (B, Tm*scale) fp32."""
+        self._chk(f0, phase, noise, lin_w, out)
+        B, Tm = f0.shape
+        H = phase.shape[1]
+        assert f0.dtype == torch.float32 and f0.stride(1) == 1 and phase.is_contiguous() and phase.shape == (B, H)
+        assert out.shape == (B, Tm * scale) and out.stride(1) == 1 and lin_w.numel() == H and lin_w.is_contiguous()
+        if noise is not None:
+            assert noise.shape == (B, H, Tm * scale) and noise.is_contiguous() and noise.dtype == torch.float32
+        ws = torch.empty(B * H * Tm, dtype=torch.float64, device=f0.device)
+        self._t0("hift_source")
+        check(self.lib.svc_hift_source(f0.data_ptr(), f0.stride(0), phase.data_ptr(), _ptr(noise), lin_w.data_ptr(),
+                                       float(lin_b), ws.data_ptr(), out.data_ptr(), out.stride(0), B, Tm, H, scale,
+                                       float(sr), float(sine_amp), float(noise_std), float(voiced_thr),
+                                       self._stream()), "svc_hift_source")
+        self._t1()
+
+    def hift_stft(self, s, out):
+        """s (B, L) fp32 -> out (B, rows, Cpad): [re | im | 0] per frame, rows beyond L/4+1 zeroed."""
+        self._chk(s, out)
+        B, L = s.shape
+        assert s.dtype == torch.float32 and s.stride(1) == 1 and out.shape[0] == B and out.stride(2) == 1
+        self._t0("hift_stft")
+        check(self.lib.svc_hift_stft(s.data_ptr(), s.stride(0), out.data_ptr(), out.stride(0), out.stride(1), B, L,
+                                     out.shape[1], out.shape[2], self._code(out.dtype), self._stream()),
+              "svc_hift_stft")
+        self._t1()
+
+    def hift_istft(self, x, wav, clip_mag=1e2, audio_limit=0.99):
+        """x (B, TT, >=18) fp32 -> wav (B, 4*(TT-1)) fp32."""
+        self._chk(x, wav)
+        B, TT, Cx = x.shape
+        assert x.dtype == torch.float32 and x.stride(2) == 1 and Cx >= 18
+        assert wav.shape == (B, 4 * (TT - 1)) and wav.stride(1) == 1 and wav.dtype == torch.float32
+        self._t0("hift_istft")
+        check(self.lib.svc_hift_istft(x.data_ptr(), x.stride(0), x.stride(1), wav.data_ptr(), wav.stride(0), B, TT,
+                                      float(clip_mag), float(audio_limit), self.precise, self._stream()),
+              "svc_hift_istft")
+        self._t1()

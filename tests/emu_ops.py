@@ -172,3 +172,49 @@ class EmuOps:
     def set_rows(self, src, dst):
         self.launches += 1
         dst.copy_(src.expand_as(dst))
+
+    # ---------------------------------------------------------------- HiFT pieces (svc_unary, svc_hift_*)
+    def unary(self, x, out, kind, slope=0.0, alpha=None):
+        self.launches += 1
+        if kind == 0:
+            y = F.leaky_relu(x, slope)
+        elif kind == 1:
+            y = F.elu(x)
+        elif kind == 2:
+            a = alpha.view(1, 1, -1)
+            y = x + (1.0 / (a + 1e-9)) * torch.sin(x * a) ** 2
+        else:
+            y = x.abs()
+        out.copy_(y)
+
+    def hift_source(self, f0, phase, noise, lin_w, lin_b, out, scale, sr, sine_amp, noise_std, voiced_thr):
+        self.launches += 1
+        B, Tm = f0.shape
+        H = phase.shape[1]
+        f0u = f0.repeat_interleave(scale, dim=1)[:, None, :]
+        F_mat = torch.cat([f0u * (i + 1) / sr for i in range(H)], dim=1)
+        cum = torch.cumsum(F_mat.double(), dim=-1).float()        # ATen's CPU cumsum accumulates fp32 in double
+        theta = 2 * 3.141592653589793 * (cum % 1)
+        ph = phase.clone().view(B, H, 1)
+        ph[:, 0] = 0
+        sine = sine_amp * torch.sin(theta + ph)
+        uv = (f0u > voiced_thr).float()
+        amp = uv * noise_std + (1 - uv) * sine_amp / 3
+        sine = sine * uv + (amp * noise if noise is not None else 0)
+        out.copy_(torch.tanh((sine * lin_w.view(1, H, 1)).sum(1) + lin_b))
+
+    def hift_stft(self, s, out):
+        self.launches += 1
+        spec = torch.stft(s, 16, 4, 16, window=torch.hann_window(16, periodic=True, device=s.device), return_complex=True)
+        TT = spec.shape[-1]
+        out.zero_()
+        out[:, :TT, 0:9] = spec.real.transpose(1, 2)
+        out[:, :TT, 9:18] = spec.imag.transpose(1, 2)
+
+    def hift_istft(self, x, wav, clip_mag=1e2, audio_limit=0.99):
+        self.launches += 1
+        mag = torch.clip(torch.exp(x[..., 0:9]), max=clip_mag).transpose(1, 2)
+        ph = torch.sin(x[..., 9:18]).transpose(1, 2)
+        y = torch.istft(torch.complex(mag * torch.cos(ph), mag * torch.sin(ph)), 16, 4, 16,
+                        window=torch.hann_window(16, periodic=True, device=x.device))
+        wav.copy_(y.clamp(-audio_limit, audio_limit))

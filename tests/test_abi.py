@@ -48,14 +48,16 @@ def test_struct_layout_matches_header():
     """sizeof(svc_gemm_desc) as the compiler sees it == the ctypes mirror."""
     import subprocess
     import tempfile
-    code = '#include <stdio.h>\n#include "seedvc_b200.h"\nint main(){printf("%zu", sizeof(svc_gemm_desc));}'
+    code = ('#include <stdio.h>\n#include "seedvc_b200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(svc_gemm_desc), '
+            'sizeof(svc_dit_weights), sizeof(svc_dit_state), sizeof(svc_bigvgan_weights));}')
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "s.c")
         open(src, "w").write(code)
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
-        n = int(subprocess.check_output([exe]).decode())
-    assert n == ctypes.sizeof(_lib.GemmDesc)
+        n = [int(v) for v in subprocess.check_output([exe]).decode().split()]
+    assert n == [ctypes.sizeof(_lib.GemmDesc), ctypes.sizeof(_lib.DitWeights), ctypes.sizeof(_lib.DitState),
+                 ctypes.sizeof(_lib.BigVGANWeights)]
 
 
 def test_missing_library_fails_loudly(tmp_path):

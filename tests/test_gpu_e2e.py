@@ -263,3 +263,98 @@ def test_mel_frontend_golden():
         assert tuple(got.shape) == z[name].shape and e < 1e-3
     with pytest.raises(RuntimeError):
         mel_spectrogram(torch.zeros(1, 4096), 1024, 80, 22050, 256, 1024, 0, None)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
+def test_hift_golden(mode):
+    """HiFTGenerator on the CUDA kernels vs the REAL reference's outputs (oracle/gen_golden_hift.py),
+    SineGen's phase / noise draws injected; the F0 predictor separately."""
+    import json
+    import os
+
+    import numpy as np
+    from seedvc_b200.hifigan import ConvRNNF0Predictor, HiFTGenerator
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "hift.npz"))
+    if "hift" not in _models:
+        _models["hift"] = HiFTGenerator(f0_predictor=ConvRNNF0Predictor()).to(DEV)
+    gen = _models["hift"]
+    gen.set_mode(mode)
+    for name, m in json.loads(str(z["meta"])).items():
+        mel = synth.synth_mel(m["B"], 80, m["Tm"], seed=m["mel_seed"]).to(DEV)
+        f0 = synth.synth_f0(m["B"], m["Tm"], seed=m["f0_seed"]).to(DEV) if m["f0_given"] else None
+        phase, noise = [t.to(DEV) for t in synth.synth_hift_noise(m["B"], 9, m["Tm"] * 256, seed=m["noise_seed"])]
+        wav = gen(mel, f0=f0, phase=phase, noise=noise)
+        e = rel_l2(wav.cpu(), z[name + "_wav"])
+        w = gen._prepare()
+        e_f0 = rel_l2(gen._predict_f0(w, w["ops"], mel).cpu(), z[name + "_f0pred"])
+        print(f"hift {name} [{mode}] waveform rel-L2 {e:.2e}  f0 predictor rel-L2 {e_f0:.2e}")
+        # 16-bit modes: the north_star tolerance (HiFT runs on IEEE-half operands in both, see hifigan.py)
+        assert tuple(wav.shape) == z[name + "_wav"].shape and e < (1e-3 if mode == "fp32" else 1e-2)
+        assert e_f0 < {"fp32": 1e-5, "fp16": 3e-3, "bf16": 3e-3}[mode]
+    out = gen.inference(synth.synth_mel(1, 80, 20).to(DEV))          # own phase / noise draws, predictor F0
+    assert out.shape == (1, 20 * 256) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("shape", [(1, 323, 258, 4), (3, 200, 60, 3)])
+def test_graphed_conversion_bit_exact(shape):
+    """graphs.GraphedConversion (one CUDA-graph replay per conversion: the launch-bound config 1 / config 5 shapes)
+    returns bit-exactly what the eager launch sequence returns, also after the inputs change between replays."""
+    from seedvc_b200.graphs import GraphedConversion
+
+    B, T, Tp, steps = shape
+    cfm, args = v1_model("xlsr_tiny", False, "bf16")
+    if "voc" not in _models:
+        _models["voc"] = BigVGAN(configs.bigvgan_h()).to(DEV)
+    voc = _models["voc"]
+    voc.set_mode("bf16")
+    g = GraphedConversion(cfm, voc, B, T, Tp, steps, 0.7)
+    t_span = torch.linspace(0, 1, steps + 1, device=DEV)
+    lens = torch.full((B,), T, device=DEV)
+    for first_id in (0, 40, 41):
+        mu, prompt, style, z = [t.to(DEV) for t in synth.synth_batch(B, T, Tp, 80, args.DiT.content_dim,
+                                                                      first_id=first_id)]
+        want = voc(cfm.solve_euler(z.clone(), lens, prompt, mu, style, None, t_span, 0.7)[:, :, Tp:].contiguous())
+        got = g(mu, lens, prompt, style, z)
+        assert torch.equal(got, want), first_id
+
+
+@pytest.mark.parametrize("model,mode", [("whisper_small", "bf16"), ("whisper_small", "fp32"), ("xlsr_tiny", "fp16"),
+                                        ("whisper_base", "bf16")])
+def test_dit_step_c_entry_point_equals_python_sequence(model, mode):
+    """svc_dit_step (one C call per estimator call, csrc/graph.cu) issues the launch sequence DiTEngine.step writes
+    out in Python: the two give bit-identical results (the Python sequence runs when per-launch profiling is on)."""
+    cfm, args = v1_model(model, True, mode)
+    T, Tp, B = 140, 33, 2
+    mu, prompt, style, z = [t.to(DEV) for t in synth.synth_batch(B, T, Tp, args.DiT.in_channels,
+                                                                  args.DiT.content_dim, first_id=21)]
+    lens = torch.tensor([T, 101], device=DEV)
+    t_span = torch.linspace(0, 1, 4, device=DEV)
+    ops = cfm.estimator.engine().ops
+    n0 = ops.launches
+    a = cfm.solve_euler(z.clone(), lens, prompt, mu, style, None, t_span, 0.7)
+    n_c = ops.launches - n0
+    ops.start_profile()
+    n0 = ops.launches
+    b = cfm.solve_euler(z.clone(), lens, prompt, mu, style, None, t_span, 0.7)
+    n_py = ops.launches - n0
+    prof = ops.stop_profile()
+    assert torch.equal(a, b)
+    assert n_c == n_py and sum(d["launches"] for d in prof.values()) == n_py
+
+
+def test_dit_step_c_entry_point_v2():
+    if "v2" not in _models:
+        _models["v2"] = CFMv2(DiTv2(**configs.v2_estimator_kwargs())).to(DEV)
+    cfm = _models["v2"]
+    cfm.set_mode("bf16")
+    kw = configs.v2_estimator_kwargs()
+    mu, prompt, style, z = [t.to(DEV) for t in synth.synth_batch(2, 90, 25, kw["in_channels"], kw["content_dim"])]
+    t_span = torch.linspace(0, 1, 3, device=DEV)
+    lens = torch.tensor([90, 77], device=DEV)
+    ops = cfm.estimator.engine().ops
+    a = cfm.solve_euler(z.clone(), lens, prompt, mu, style, t_span, [0.7, 0.7], False)
+    ops.start_profile()
+    b = cfm.solve_euler(z.clone(), lens, prompt, mu, style, t_span, [0.7, 0.7], False)
+    ops.stop_profile()
+    assert torch.equal(a, b)

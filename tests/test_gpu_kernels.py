@@ -204,6 +204,42 @@ def test_attention(mode, simt, B, T, H, lens):
     assert e < (1e-5 if mode == "fp32" else 6e-3), f"rel-L2 {e}"
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+@pytest.mark.parametrize("pattern", ["late_x40", "late_x8", "early_x40", "one_outlier_key", "ramp"])
+def test_attention_score_range(mode, pattern):
+    """Score ranges that stress the running reference max of the tensor-core kernel: in bf16 mode later key blocks do
+    not look for a new row max unless the block sum / the polynomial-exp2 elements signal an exponent-range threat
+    (attention.cu, lazy max) - keys whose scores exceed everything seen before by 10 ... 250 log2 units must still give
+    the softmax of the reference."""
+    ops, emu = ops_for(mode), EmuOps()
+    od = ops.op_dtype
+    B, T, H = 2, 700, 2
+    D = H * 64
+    qkv = rnd(B, T, 3 * D, seed=77, dtype=torch.float32)
+    qkv[..., :D] *= 0.125
+    k = qkv[..., D:2 * D]
+    if pattern == "late_x40":
+        k[:, 300:] *= 40.0
+    elif pattern == "late_x8":
+        k[:, 450:] *= 8.0
+    elif pattern == "early_x40":
+        k[:, :64] *= 40.0
+    elif pattern == "one_outlier_key":
+        k[:, 517] *= 60.0
+    else:
+        k *= torch.linspace(0.5, 30.0, T, device=DEV).view(1, T, 1)
+    qkv = qkv.to(od)
+    kv = torch.tensor([T, 613], dtype=torch.int32, device=DEV)
+    out = torch.zeros(B, T, D, dtype=od, device=DEV)
+    ref = torch.zeros(B, T, D, device=DEV)
+    ops.attention(qkv, out, H, kv)
+    emu.attention(qkv.float(), ref, H, kv)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    e = rel_l2(out.float(), ref)
+    assert e < 6e-3, f"{pattern} rel-L2 {e}"
+
+
 @pytest.mark.parametrize("D", [128, 384, 512, 768])
 @pytest.mark.parametrize("mode", ["bf16", "fp16", "fp32"])
 def test_norm_mod(D, mode):
@@ -224,6 +260,11 @@ def test_norm_mod(D, mode):
         ops.norm_mod(x, out2, raw_out=raw, **kw)
         assert torch.equal(out2, out)
         assert torch.equal(raw, x.to(ops.op_dtype))
+        if mode != "fp32":   # raw copy in the other 16-bit format (bf16 mode keeps stream copies in IEEE half)
+            other = torch.float16 if ops.op_dtype == torch.bfloat16 else torch.bfloat16
+            raw2 = torch.zeros(B, T, D, dtype=other, device=DEV)
+            ops.norm_mod(x, out2, raw_out=raw2, **kw)
+            assert torch.equal(out2, out) and torch.equal(raw2, x.to(other))
 
 
 @pytest.mark.parametrize("C,L", [(24, 1000), (48, 515), (96, 300), (768, 70), (192, 129), (16, 40),
@@ -420,3 +461,58 @@ def test_sola_stitch_non_finite_inputs():
                 continue       # finite streams are covered bit-exactly by test_sola_stitch_streams
             assert int(offs[s]) == int(torch.argmax(c)), (where, s, int(offs[s]), int(torch.argmax(c)))
         assert out.shape == (3, block)
+
+
+# --------------------------------------------------------------------------------------------- HiFT pieces
+@pytest.mark.parametrize("mode", ["bf16", "fp16", "fp32"])
+def test_hift_unary(mode):
+    ops, emu = ops_for(mode), EmuOps()
+    B, T, C = 2, 131, 96
+    x = rnd(B, T + 1, C, seed=4, scale=2.0)[:, 1:, :]                # strided rows
+    alpha = (1.0 + 0.25 * rnd(C, seed=5)).clamp_min(0.3)
+    for kind, kw in ((0, dict(slope=0.1)), (1, {}), (2, dict(alpha=alpha)), (3, {})):
+        out = torch.zeros(B, T, C, dtype=ops.op_dtype, device=DEV)
+        ref = torch.zeros(B, T, C, device=DEV)
+        ops.unary(x, out, kind, **kw)
+        emu.unary(x, ref, kind, **kw)
+        assert rel_l2(out.float(), ref) < {"fp32": 1e-6, "bf16": 4e-3, "fp16": 6e-4}[mode], (kind, mode)
+
+
+def test_hift_source_stft_istft():
+    """svc_hift_source / svc_hift_stft / svc_hift_istft (fp32) vs the torch restatement (torch.cumsum in double,
+    torch.stft, torch.istft): source within 2e-5 (the phase accumulators are reproduced in closed form), STFT / iSTFT
+    at fp32 round-off."""
+    from seedvc_b200 import synth
+    ops, emu = ops_for("fp32"), EmuOps()
+    B, Tm, H, scale = 3, 37, 9, 256
+    f0 = synth.synth_f0(B, Tm, seed=8).to(DEV)
+    phase, noise = [t.to(DEV) for t in synth.synth_hift_noise(B, H, Tm * scale, seed=9)]
+    lw, lb = rnd(H, seed=1, scale=0.4), 0.05
+    s, s_ref = torch.zeros(B, Tm * scale, device=DEV), torch.zeros(B, Tm * scale, device=DEV)
+    # the restatement runs on the CPU like the reference's source does in the goldens: on CUDA, ATen turns
+    # `tensor / python_scalar` into a multiplication by the reciprocal, which moves F0 * h / sr by an ulp
+    s_cpu = torch.zeros(B, Tm * scale)
+    ops.hift_source(f0, phase.reshape(B, H).contiguous(), noise, lw, lb, s, scale, 22050, 0.1, 0.003, 10)
+    emu.hift_source(f0.cpu(), phase.reshape(B, H).cpu(), noise.cpu(), lw.cpu(), lb, s_cpu, scale, 22050, 0.1, 0.003, 10)
+    assert rel_l2(s.cpu(), s_cpu) < 2e-5
+    ops.hift_source(f0, phase.reshape(B, H).contiguous(), None, lw, lb, s, scale, 22050, 0.1, 0.003, 10)
+    emu.hift_source(f0.cpu(), phase.reshape(B, H).cpu(), None, lw.cpu(), lb, s_cpu, scale, 22050, 0.1, 0.003, 10)
+    assert rel_l2(s.cpu(), s_cpu) < 2e-5
+    s_ref.copy_(s_cpu)
+    TT = Tm * scale // 4 + 1
+    rows = 8 * (TT // 8 + 2)
+    buf = torch.full((B, rows, 24), 7.0, device=DEV)
+    ref = torch.zeros(B, rows, 24, device=DEV)
+    ops.hift_stft(s_ref, buf)
+    emu.hift_stft(s_ref, ref)
+    assert rel_l2(buf, ref) < 1e-5 and float(buf[:, TT:].abs().max()) == 0.0 and float(buf[..., 18:].abs().max()) == 0.0
+    x = rnd(B, TT, 24, seed=12, scale=0.7)
+    x[..., :9] -= 1.0
+    wav, wref = torch.zeros(B, 4 * (TT - 1), device=DEV), torch.zeros(B, 4 * (TT - 1), device=DEV)
+    ops.hift_istft(x, wav)
+    emu.hift_istft(x, wref)
+    assert rel_l2(wav, wref) < 1e-5
+    x[..., :9] += 8.0                                                # drives exp() past the 1e2 magnitude clip and the clamp
+    ops.hift_istft(x, wav)
+    emu.hift_istft(x, wref)
+    assert rel_l2(wav, wref) < 1e-5 and float(wav.abs().max()) <= 0.99 + 1e-7

@@ -142,3 +142,87 @@ def test_nearest_index_matches_aten():
         want = F.interpolate(src, size=n_out, mode="nearest").view(-1).long().numpy()
         got = nearest_index(n_in, n_out)
         assert (got == want).all(), (n_in, n_out)
+
+
+def _hift_case(name, m):
+    import seedvc_oracle as orc
+    mel = synth.synth_mel(m["B"], 80, m["Tm"], seed=m["mel_seed"])
+    f0 = synth.synth_f0(m["B"], m["Tm"], seed=m["f0_seed"]) if m["f0_given"] else None
+    phase, noise = synth.synth_hift_noise(m["B"], orc.HIFT_CFG["nb_harmonics"] + 1, m["Tm"] * 256, seed=m["noise_seed"])
+    return mel, f0, phase, noise
+
+
+def test_hift_host_logic():
+    """HiFTGenerator's orchestration (weight-norm folding, polyphase upsamplers, stride-8 source conv as a
+    regrouped 3-tap GEMM, reflection pad, epilogue-fused sums) on the emulated ops vs the REAL reference's outputs."""
+    import json
+    import os
+
+    import numpy as np
+    from seedvc_b200.hifigan import ConvRNNF0Predictor, HiFTGenerator
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "hift.npz"))
+    gen = HiFTGenerator(f0_predictor=ConvRNNF0Predictor())
+    w = gen._build_weights(EmuOps())
+    gen._prepare = lambda: w
+    for name, m in json.loads(str(z["meta"])).items():
+        mel, f0, phase, noise = _hift_case(name, m)
+        wav = gen(mel, f0=f0, phase=phase, noise=noise)
+        assert wav.shape == z[name + "_wav"].shape
+        e = rel_l2(wav, z[name + "_wav"])
+        assert e < 1e-4, (name, e)
+        f0p = gen._predict_f0(w, w["ops"], mel)
+        assert rel_l2(f0p, z[name + "_f0pred"]) < 1e-5
+
+
+def test_hift_oracle_matches_reference(manifest):
+    """oracle.hift_forward / hift_f0_predictor vs the REAL HiFTGenerator (oracle/gen_golden_hift.py)."""
+    import json
+    import os
+
+    import numpy as np
+    import seedvc_oracle as orc
+
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "hift.npz"))
+    sd = synth.synth_state_dict(manifest["keys_hift"])
+    for name, m in json.loads(str(z["meta"])).items():
+        mel, f0, phase, noise = _hift_case(name, m)
+        wav = orc.hift_forward(sd, mel, phase, noise, f0=f0)
+        assert rel_l2(wav, z[name + "_wav"]) < 2e-5, name
+        assert rel_l2(orc.hift_f0_predictor(sd, mel), z[name + "_f0pred"]) < 2e-5
+
+
+@pytest.mark.parametrize("model,cfg", [("whisper_small", 0.7), ("xlsr_tiny", 0.7), ("whisper_base", 0.0), ("v2", (0.7, 0.7))])
+def test_launches_per_step_bookkeeping(model, cfg):
+    """DiTEngine.launches_per_step (what the one-call C path adds to the launch counter) == the number of ops the
+    written-out Python sequence issues for one estimator call."""
+    T, Tp = 40, 10
+    if model == "v2":
+        kw = configs.v2_estimator_kwargs()
+        kw.update(hidden_dim=128, num_heads=2, depth=3, content_dim=128)
+        cfm = CFMv2(DiTv2(**kw))
+        C, cd = kw["in_channels"], kw["content_dim"]
+    else:
+        args = configs.scaled_down(configs.v1_model_params(model))
+        cfm = CFM(args)
+        C, cd = args.DiT.in_channels, args.DiT.content_dim
+    eng = emu_engine(cfm.estimator)
+    if model != "v2":
+        cfm.estimator.setup_caches(1, 8192)
+    counts = []
+    orig = eng.step
+
+    def counting(s, x_op):
+        n0 = eng.ops.launches
+        v = orig(s, x_op)
+        counts.append(eng.ops.launches - n0)
+        return v
+
+    eng.step = counting
+    mu, prompt, style, z = synth.synth_batch(2, T, Tp, C, cd)
+    t_span = torch.linspace(0, 1, 3)
+    if model == "v2":
+        cfm.solve_euler(z, torch.tensor([T, T]), prompt, mu, style, t_span, list(cfg), False)
+    else:
+        cfm.solve_euler(z, torch.tensor([T, T]), prompt, mu, style, None, t_span, cfg)
+    assert counts and all(c == eng.launches_per_step() for c in counts), (counts, eng.launches_per_step())
