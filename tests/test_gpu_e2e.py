@@ -358,3 +358,26 @@ def test_dit_step_c_entry_point_v2():
     b = cfm.solve_euler(z.clone(), lens, prompt, mu, style, t_span, [0.7, 0.7], False)
     ops.stop_profile()
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_bigvgan_c_entry_point_equals_python_sequence(mode):
+    """svc_bigvgan_forward (one C call, csrc/graph.cu) == the launch sequence BigVGAN.forward writes out in Python
+    (which runs when per-launch profiling is on), bit for bit, for both vocoder configs."""
+    for key, cfgname, Tm in (("voc", "bigvgan_22k", 23), ("voc44", "bigvgan_44k", 9)):
+        if key not in _models:
+            _models[key] = BigVGAN(configs.bigvgan_h(cfgname)).to(DEV)
+        voc = _models[key]
+        voc.set_mode(mode)
+        mel = synth.synth_mel(2, voc.h.num_mels, Tm, seed=5).to(DEV)
+        ops = voc._prepare()["ops"]
+        n0 = ops.launches
+        a = voc(mel)
+        n_c = ops.launches - n0
+        ops.start_profile()
+        n0 = ops.launches
+        b = voc(mel)
+        n_py = ops.launches - n0
+        ops.stop_profile()
+        assert voc._prepare()["c"] is not None
+        assert torch.equal(a, b) and n_c == n_py
