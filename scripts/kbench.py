@@ -52,6 +52,8 @@ if "gemm" in what:
     tab = rope_table(M_T + 4).to(DEV)
     cases = [
         ("qkv  K512 N1536 rope->bf16", [D], 3 * D, dict(act=_lib.ACT_ROPE, rope=(tab, 2 * D, 0, D, 0.125)), "op"),
+        ("qkvN K512 N1536 plain->bf16", [D], 3 * D, dict(), "op"),
+        ("qkvB K512 N1536 bias->bf16", [D], 3 * D, dict(bias=True), "op"),
         ("wo   K512 N512 +res->f32", [D], D, dict(res=True), "f32"),
         ("w13  K512 N3072 swiglu->bf16", [D], 2 * I, dict(act=_lib.ACT_SWIGLU_PAIR), "op"),
         ("w2   K1536 N512 +res->f32", [I], D, dict(res=True), "f32"),
@@ -75,6 +77,8 @@ if "gemm" in what:
         kws = dict(kw)
         if kws.pop("res", False):
             kws["res"] = torch.randn(M_B, M_T, n_out, device=DEV)
+        if kws.pop("bias", False):
+            kws["bias"] = torch.randn(N, device=DEV)
         of = torch.empty(M_B, M_T, n_out, device=DEV) if outk in ("f32", "both") else None
         oo = torch.empty(M_B, M_T, n_out, dtype=torch.bfloat16, device=DEV) if outk in ("op", "both") else None
         if "res" in kws and of is not None:

@@ -82,11 +82,15 @@ if os.path.exists(path):
 
 # ---- full captures ---------------------------------------------------------------------------
 for rep in sorted(os.listdir(OUT)):
-    if not rep.endswith(".ncu-rep") or rep == "prof_k.ncu-rep":
+    if rep.endswith("_raw.csv"):               # exported on the GPU box (scripts/gpu_ncu.sh: export_rep)
+        text = open(os.path.join(OUT, rep)).read()
+        rep = rep.replace("_raw.csv", ".ncu-rep")
+    elif rep.endswith(".ncu-rep") and rep != "prof_k.ncu-rep":
+        text = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"],
+                              capture_output=True, text=True).stdout
+    else:
         continue
-    p = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"],
-                       capture_output=True, text=True)
-    rows = list(csv.reader(p.stdout.splitlines()))
+    rows = list(csv.reader(text.splitlines()))
     if len(rows) < 3:
         continue
     hdr, units = rows[0], rows[1]
