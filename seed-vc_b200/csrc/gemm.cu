@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "epilogue.cuh"
 
@@ -490,14 +491,34 @@ __device__ __forceinline__ void res_prefetch_rows(const EpiParams& e, int c0, in
 // 128B rows, SWIZZLE_128B) - no transpose round trip through shared memory.  Interleaved-pair RoPE
 // works here because a pair sits in adjacent registers; its table must be pair-major so that the 32
 // rows of a warp read consecutive addresses (rr = 16 (cos, sin) pairs prefetched one item ahead).
-template <bool PAIR>
+//
+// EK (epilogue kind) resolves the launch-constant questions at compile time.  An epilogue warp runs alone on its
+// scheduler slot, so every warp-uniform branch on a kernel parameter costs its full latency; clock stamps showed
+// ~500 of the ~1 500 cycles of a 32-column item going to the dozen "is there a bias / gate / residual / alpha"
+// branches.  The kernel picks EK once (epi_kind) and runs the item loop specialised for it:
+//   0 generic (every check at run time)      1 no vector operand; act = none or (pair) SwiGLU
+//   2 interleaved-pair RoPE, nothing else     3 bias only (+ row-layout residual in the two-output epilogue)
+//   4 per-batch bias + tanh * sigmoid pair (WaveNet in-layers)
+constexpr int EK_GENERIC = 0, EK_PLAIN = 1, EK_ROPE = 2, EK_BIAS = 3, EK_ROWBIAS_TS = 4;
+
+template <bool PAIR, int EK, bool DUAL>
 __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* stage, int lane, int b,
                                                      int t_base, int n0_acc, float (&v)[PAIR ? 64 : 32],
                                                      const float4 (&rr)[8]) {
     const EpiParams& e = p.epi;
     constexpr int NA = PAIR ? 64 : 32;
+    constexpr bool G = EK == EK_GENERIC;
     const int c0 = PAIR ? (n0_acc >> 1) : n0_acc;          // first output column
-    if (e.bias != nullptr) {
+    const bool has_bias = G ? e.bias != nullptr : EK == EK_BIAS;
+    const bool has_rowbias = G ? e.rowbias != nullptr : EK == EK_ROWBIAS_TS;
+    const bool has_gate = G ? e.gate != nullptr : false;
+    const bool has_res = G ? p.res_rows != 0 : (EK == EK_BIAS && DUAL && p.res_rows != 0);
+    const bool has_alpha = G ? e.alpha != 1.0f : false;
+    const int act = G ? e.act
+                      : EK == EK_ROPE ? SVC_ACT_ROPE
+                      : EK == EK_ROWBIAS_TS ? SVC_ACT_TANH_SIG_PAIR
+                      : (EK == EK_PLAIN && PAIR) ? SVC_ACT_SWIGLU_PAIR : SVC_ACT_NONE;
+    if (has_bias) {
 #pragma unroll
         for (int j = 0; j < NA; j += 4)
             if (n0_acc + j < e.N) {
@@ -505,7 +526,7 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
                 v[j] += q.x, v[j + 1] += q.y, v[j + 2] += q.z, v[j + 3] += q.w;
             }
     }
-    if (e.rowbias != nullptr) {
+    if (has_rowbias) {
         const float* rb = e.rowbias + static_cast<long long>(b) * e.rowbias_bstride + n0_acc;
 #pragma unroll
         for (int j = 0; j < NA; j += 4)
@@ -514,16 +535,16 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
                 v[j] += q.x, v[j + 1] += q.y, v[j + 2] += q.z, v[j + 3] += q.w;
             }
     }
-    if (e.act == SVC_ACT_SILU) {
+    if (act == SVC_ACT_SILU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(v[j]);
-    } else if (PAIR && e.act == SVC_ACT_SWIGLU_PAIR) {
+    } else if (PAIR && act == SVC_ACT_SWIGLU_PAIR) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = v[2 * j] * fast_sigmoid(v[2 * j]) * v[2 * j + 1];
-    } else if (PAIR && e.act == SVC_ACT_TANH_SIG_PAIR) {
+    } else if (PAIR && act == SVC_ACT_TANH_SIG_PAIR) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[2 * j]) * fast_sigmoid(v[2 * j + 1]);
-    } else if (!PAIR && e.act == SVC_ACT_ROPE && c0 < e.rope_cols) {
+    } else if (!PAIR && act == SVC_ACT_ROPE && c0 < e.rope_cols) {
         const float qs = c0 < e.q_cols ? e.q_scale : 1.0f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -535,7 +556,7 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
             v[4 * i + 3] = (x3 * cs.z + x2 * cs.w) * qs;
         }
     }
-    if (e.gate != nullptr) {
+    if (has_gate) {
         const float* gp = e.gate + static_cast<long long>(b) * e.gate_bstride + c0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -544,12 +565,12 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
                 v[j] *= q.x, v[j + 1] *= q.y, v[j + 2] *= q.z, v[j + 3] *= q.w;
             }
     }
-    if (!PAIR && p.res_rows) {
+    if (!PAIR && has_res) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             v[4 * q] += rr[q].x, v[4 * q + 1] += rr[q].y, v[4 * q + 2] += rr[q].z, v[4 * q + 3] += rr[q].w;
     }
-    if (e.alpha != 1.0f) {
+    if (has_alpha) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
     }
@@ -557,8 +578,8 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     if (lane == 0) bulk_wait_read0();
     __syncwarp();
     uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
-    if (p.store_mode == 1 || p.dual) {
-        uint8_t* row = sb + (p.dual ? 4096 : 0) + lane * 64;
+    if (p.store_mode == 1 || DUAL) {
+        uint8_t* row = sb + (DUAL ? 4096 : 0) + lane * 64;
         const int sw = (lane >> 1) & 3;
         if (e.op_is_f16) {         // warp-uniform: one conversion flavour per launch
 #pragma unroll
@@ -587,9 +608,24 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     if (lane == 0) {
         if (p.store_mode == 2) tma_reduce_add_3d(&p.omap, stage, c0, t_base, b);
         else tma_store_3d(&p.omap, stage, c0, t_base, b);
-        if (p.dual) tma_store_3d(&p.omap2, sb + 4096, c0, t_base, b);
+        if (DUAL) tma_store_3d(&p.omap2, sb + 4096, c0, t_base, b);
         bulk_commit();
     }
+}
+
+// Which specialised item loop a launch can use (warp-uniform, evaluated once per kernel)
+__device__ __forceinline__ int epi_kind(const TcParams& p, bool pair, bool dual) {
+    const EpiParams& e = p.epi;
+    if (e.gate != nullptr || e.alpha != 1.0f) return EK_GENERIC;
+    const bool b = e.bias != nullptr, rb = e.rowbias != nullptr, rs = p.res_rows != 0;
+    if (!b && !rb && !rs) {
+        if (!pair && e.act == SVC_ACT_NONE) return EK_PLAIN;
+        if (pair && e.act == SVC_ACT_SWIGLU_PAIR) return EK_PLAIN;
+        if (!pair && e.act == SVC_ACT_ROPE) return EK_ROPE;
+    }
+    if (b && !rb && !pair && e.act == SVC_ACT_NONE && (dual || !rs)) return EK_BIAS;
+    if (rb && !b && !rs && pair && e.act == SVC_ACT_TANH_SIG_PAIR) return EK_ROWBIAS_TS;
+    return EK_GENERIC;
 }
 
 // Persistent, warp-specialised tcgen05 GEMM.  One CTA per SM walks output tiles
@@ -770,17 +806,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         // geometry used by the prefetch (4 columns per lane, 8 steps) in TMA mode
         EpiChunk g_tma;
         g_tma.co = 32, g_tma.lanes_per_row = 8, g_tma.rows_per_it = 4, g_tma.n_it = 8, g_tma.vec = true;
+        // the item loop, specialised on the epilogue kind (see epilogue_item_direct); EK != 0 only for direct EPIs
+        auto run_items = [&](auto ek_tag) {
+        constexpr int EK = decltype(ek_tag)::value;
         Item cur = make_item(group, 0);
-        EpiChunk g_cur = epi_chunk_geom(p.epi, cur.n0c);
-        if constexpr (tma_mode) { g_cur = g_tma; g_cur.c0 = pair ? (cur.n0c >> 1) : cur.n0c; }
+        EpiChunk g_cur = g_tma;
+        if constexpr (tma_mode) g_cur.c0 = pair ? (cur.n0c >> 1) : cur.n0c;
+        else g_cur = epi_chunk_geom(p.epi, cur.n0c);
         float4 rr_cur[8], rr_nxt[8];
-        const bool want_prefetch = !direct && (!tma_mode || p.epi.act == SVC_ACT_ROPE);
-        const bool rope_direct = direct && p.epi.act == SVC_ACT_ROPE;
+        const bool want_prefetch = EK == EK_GENERIC && !direct && (!tma_mode || p.epi.act == SVC_ACT_ROPE);
+        const bool rope_direct = EK == EK_GENERIC ? (direct && p.epi.act == SVC_ACT_ROPE) : EK == EK_ROPE;
         if (cur.valid && want_prefetch && g_cur.vec && cur.t_base < p.T)
             epi_prefetch(p.epi, g_cur, lane, cur.b, cur.t_base, p.T, rr_cur);
         if (rope_direct && cur.valid && cur.n0c < p.epi.rope_cols)
             rope_prefetch_rows(p.epi, cur.n0c, lane, cur.t_base, rr_cur);
-        const bool res_direct = direct && !pair && p.res_rows;
+        const bool res_direct = EK == EK_GENERIC ? (direct && !pair && p.res_rows)
+                                                 : (EK == EK_BIAS && EPI == 5 && p.res_rows);
         if (res_direct && cur.valid) res_prefetch_rows(p.epi, cur.n0c, lane, cur.b, cur.t_base, p.T, rr_cur);
         int tr_i = 0;
         const bool tr_on = (warp == 2 && lane == 0);
@@ -794,8 +835,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             tmem_ld_32x32(taddr + cur.ch * acc_per_item, r);
             if constexpr (pair) tmem_ld_32x32(taddr + cur.ch * 64 + 32, r2);
             const Item nxt = next_item(cur);
-            EpiChunk g_nxt = epi_chunk_geom(p.epi, nxt.n0c);
-            if constexpr (tma_mode) { g_nxt = g_tma; g_nxt.c0 = pair ? (nxt.n0c >> 1) : nxt.n0c; }
+            EpiChunk g_nxt = g_tma;
+            if constexpr (tma_mode) g_nxt.c0 = pair ? (nxt.n0c >> 1) : nxt.n0c;
+            else g_nxt = epi_chunk_geom(p.epi, nxt.n0c);
             if (nxt.valid && want_prefetch && g_nxt.vec && nxt.t_base < p.T && !(SVC_DBG_BITS(p) & 32))
                 epi_prefetch(p.epi, g_nxt, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
             if (rope_direct && nxt.valid && nxt.n0c < p.epi.rope_cols) {
@@ -827,13 +869,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     float v[64];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]), v[32 + j] = __uint_as_float(r2[j]);
-                    if constexpr (direct) epilogue_item_direct<true>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                    if constexpr (direct) epilogue_item_direct<true, EK, EPI == 5>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
                     else epilogue_item_tma<true>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
                 } else {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if constexpr (direct) epilogue_item_direct<false>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                    if constexpr (direct) epilogue_item_direct<false, EK, EPI == 5>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
                     else epilogue_item_tma<false>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
                 }
             }
@@ -843,6 +885,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             g_cur = g_nxt;
 #pragma unroll
             for (int i = 0; i < 8; ++i) rr_cur[i] = rr_nxt[i];
+        }
+        };   // run_items
+        using ek0 = std::integral_constant<int, EK_GENERIC>;
+        int ek = EK_GENERIC;
+        if constexpr (direct) ek = epi_kind(p, pair, EPI == 5);
+        if (EPI != 5 && ek == EK_PLAIN) {
+            if constexpr (direct && EPI != 5) run_items(std::integral_constant<int, EK_PLAIN>{});
+        } else if (EPI == 3 && ek == EK_ROPE) {
+            if constexpr (EPI == 3) run_items(std::integral_constant<int, EK_ROPE>{});
+        } else if ((EPI == 3 || EPI == 5) && ek == EK_BIAS) {
+            if constexpr (EPI == 3 || EPI == 5) run_items(std::integral_constant<int, EK_BIAS>{});
+        } else if (EPI == 4 && ek == EK_ROWBIAS_TS) {
+            if constexpr (EPI == 4) run_items(std::integral_constant<int, EK_ROWBIAS_TS>{});
+        } else {
+            run_items(ek0{});
         }
         if (tma_mode && lane == 0) bulk_wait_read0();   // smem must outlive the last bulk store
     }

@@ -516,3 +516,67 @@ def test_hift_source_stft_istft():
     ops.hift_istft(x, wav)
     emu.hift_istft(x, wref)
     assert rel_l2(wav, wref) < 1e-5 and float(wav.abs().max()) <= 0.99 + 1e-7
+
+
+def test_guard_bands_untouched():
+    """Poor man's memcheck (compute-sanitizer is closed on this pool): every output tensor of the tensor-core GEMM
+    (all store paths), attention, norm, Snake and CFG+Euler kernels is a slice of a larger buffer whose bands before
+    and after are filled with a sentinel; ragged shapes (T not a multiple of the 128-row tile, N not a multiple of
+    the column tile) must leave the bands bit-identical."""
+    G = 4096
+    SENT = 1234.5
+
+    def guarded(shape, dtype):
+        n = 1
+        for s_ in shape:
+            n *= s_
+        big = torch.full((n + 2 * G,), SENT, dtype=dtype, device=DEV)
+        return big, big[G:G + n].view(*shape)
+
+    def intact(big, n):
+        return bool((big[:G] == SENT).all()) and bool((big[G + n:] == SENT).all())
+
+    for mode in ("bf16", "fp16"):
+        ops = ops_for(mode)
+        od = ops.op_dtype
+        B, T = 2, 257
+        for N, K, kw, kind in ((384, 128, dict(), "op"), (512, 128, dict(act=2), "op"), (256, 128, dict(), "f32"),
+                               (256, 128, dict(res=True), "f32"), (96, 96, dict(), "both"), (80, 512, dict(), "f32"),
+                               (24, 24, dict(), "f32")):
+            A = rnd(B, T, K, seed=1, dtype=od)
+            W = rnd(N, K, seed=2, scale=0.1, dtype=od)
+            n_out = N // 2 if kw.get("act") in (2, 3) else N
+            big_f, of = guarded((B, T, n_out), torch.float32)
+            big_o, oo = guarded((B, T, n_out), od)
+            kws = dict(kw)
+            if kws.pop("res", False):
+                of.copy_(rnd(B, T, n_out, seed=3))
+                kws["res"] = of                              # in-place residual (TMA reduce-add path)
+            ops.gemm([(A, 0, W)], N, B=B, T=T, out_f32=of if kind in ("f32", "both") else None,
+                     out_op=oo if kind in ("op", "both") else None, **kws)
+            torch.cuda.synchronize()
+            assert intact(big_f, of.numel()) and intact(big_o, oo.numel()), (mode, N, K, kw, kind)
+        H, Ta = 2, 323
+        qkv = rnd(B, Ta, 3 * H * 64, seed=5, dtype=od)
+        big, out = guarded((B, Ta, H * 64), od)
+        ops.attention(qkv, out, H, torch.tensor([Ta, 200], dtype=torch.int32, device=DEV))
+        torch.cuda.synchronize()
+        assert intact(big, out.numel())
+        x = rnd(B, T, 384, seed=6)
+        big, out = guarded((B, T, 384), od)
+        big_r, raw = guarded((B, T, 384), od)
+        ops.norm_mod(x, out, gamma=rnd(384, seed=7), raw_out=raw)
+        torch.cuda.synchronize()
+        assert intact(big, out.numel()) and intact(big_r, raw.numel())
+        xs = rnd(B, 1001, 48, seed=8)
+        big, out = guarded((B, 1001, 48), od)
+        ops.snake(xs, out, torch.ones(48, device=DEV), torch.ones(48, device=DEV))
+        torch.cuda.synchronize()
+        assert intact(big, out.numel())
+        big_x, xx = guarded((B, 101, 80), torch.float32)
+        xx.copy_(rnd(B, 101, 80, seed=9))
+        big_o, xo = guarded((B, 101, 80), od)
+        ops.cfg_euler(xx, rnd(2 * B, 101, 80, seed=10), [1.7, -0.7], 0.04, 9,
+                      torch.tensor([101, 64], dtype=torch.int32, device=DEV), xo)
+        torch.cuda.synchronize()
+        assert intact(big_x, xx.numel()) and intact(big_o, xo.numel())
