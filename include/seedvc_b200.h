@@ -144,8 +144,10 @@ int svc_norm_mod_copy(const float* x, long long x_bstride, long long x_rstride, 
  * FIR low-pass + 2x downsample.  Replaces Activation1d (alias_free_activation/torch/act.py:25-30,
  * resample.py:29-38, filter.py:94-101, activations.py:107-119) and the reference's own CUDA op
  * (alias_free_activation/cuda/anti_alias_activation_cuda.cu:44-179).
- * x: contiguous (B, L, C), fp32 or bf16 (x_dtype); out: contiguous (B, L, C) out_dtype.
+ * x: contiguous (B, L, C), fp32 / bf16 / fp16 (x_dtype); out: contiguous (B, L, C) out_dtype.
  * a[c] = exp(alpha_c) (or alpha_c), inv_b[c] = 1 / (beta_c + 1e-9), prepared by the caller.
+ * precise = 1 (libm sinf, fp32 FIRs) needs fp32 in and out.  With a 16-bit out_dtype and C % 8 == 0 both
+ * FIRs run on the tensor cores (x and the activated 2x signal enter them as IEEE half, taps split hi + lo).
  * ------------------------------------------------------------------------- */
 int svc_snake_aa(const void* x, int x_dtype, void* out, int out_dtype, const float* a,
                  const float* inv_b, int B, int L, int C, int precise, void* stream);

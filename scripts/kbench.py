@@ -110,6 +110,10 @@ if "snake" in what:
         ib = torch.rand(ch, device=DEV) + 0.5
         ms = timeit(lambda: ops.snake(x, out, a, ib), n=5)
         print(f"snake ch={ch:4d} L={L:7d}: {ms:8.3f} ms  {Bv * L * ch * 6 / ms / 1e6:7.0f} GB/s")
+        xh = x.half()
+        ms = timeit(lambda: ops.snake(xh, out, a, ib), n=5)
+        print(f"snake ch={ch:4d} L={L:7d} half in: {ms:8.3f} ms  {Bv * L * ch * 4 / ms / 1e6:7.0f} GB/s")
+        del xh
 
 if "norm" in what:
     x = torch.randn(64, 2580, 512, device=DEV)

@@ -103,9 +103,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    if "--variant" in sys.argv:
+    if "--variant" in sys.argv:      # --variant <tag> [--sources a.cu,b.cu] DEFINE ...
         i = sys.argv.index("--variant")
-        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        rest = sys.argv[i + 2:]
+        srcs = ("attention.cu",)
+        if rest and rest[0] == "--sources":
+            srcs, rest = tuple(rest[1].split(",")), rest[2:]
+        print(build_variant(sys.argv[i + 1], rest, srcs))
     elif "--trace" in sys.argv:
         print(build_trace())
     else:

@@ -325,7 +325,9 @@ class BigVGAN(nn.Module):
                      B=B, T=L, bias=st["up_b"], out_f32=xs.view(B, L, u * O))
             L = L * u
             act = torch.empty(B, L, O, dtype=od, device=dev)
-            xt = torch.empty(B, L, O, dtype=f32, device=dev)
+            # conv1's output feeds only the pair's second Snake, whose tensor-core FIRs read IEEE half: in the
+            # 16-bit modes the conv epilogue writes it once, as half (no fp32 round trip)
+            xt = torch.empty(B, L, O, dtype=f32 if od == f32 else torch.float16, device=dev)
             y = torch.empty(B, L, O, dtype=f32, device=dev)
             nxt = torch.empty(B, L, O, dtype=f32, device=dev)
             last_stage = si == len(w["stages"]) - 1
@@ -343,8 +345,8 @@ class BigVGAN(nn.Module):
                     ops.snake(src, act, *pr["a1"])
                     sg, f = segs_of(c1, act)
                     fl = 2.0 * B * L * O * O            # algorithmic FLOPs per tap of the original conv
-                    ops.gemm(sg, O * f, B=B, T=L // f, bias=c1["b"], out_f32=xt.view(B, L // f, O * f),
-                             algo_flops=fl * c1["k"])
+                    xo = {"out_f32" if od == f32 else "out_op": xt.view(B, L // f, O * f)}
+                    ops.gemm(sg, O * f, B=B, T=L // f, bias=c1["b"], algo_flops=fl * c1["k"], **xo)
                     ops.snake(xt, act, *pr["a2"])
                     sg, f = segs_of(c2, act)
                     vw = (B, L // f, O * f)

@@ -298,7 +298,7 @@ VocLayout voc_layout(const svc_bigvgan_weights* w, int B, int Tm) {
 }
 
 int voc_conv(const svc_conv_plan& c, int dtype, const void* act, int B, long long L, int O, const float* res, float alpha,
-             int accumulate, float* out_f32, void* out_op, void* stream) {
+             int accumulate, float* out_f32, void* out_op, int out_op_dtype, void* stream) {
     const int f = c.f;
     const int N = O * f;
     const long long rows = L / f;
@@ -308,8 +308,8 @@ int voc_conv(const svc_conv_plan& c, int dtype, const void* act, int B, long lon
     g.bias(c.b);
     if (res != nullptr) g.res(res, rows * N, N);
     g.d.alpha = alpha, g.d.accumulate = accumulate;
-    g.out_f32(out_f32, rows * N, N);
-    if (out_op != nullptr) g.out_op(out_op, rows * N, N, dtype);
+    if (out_f32 != nullptr) g.out_f32(out_f32, rows * N, N);
+    if (out_op != nullptr) g.out_op(out_op, rows * N, N, out_op_dtype);
     return g.run(stream);
 }
 
@@ -342,7 +342,10 @@ extern "C" int svc_bigvgan_forward(const svc_bigvgan_weights* w, const float* me
         RUN(g.run(stream));
     }
     float* xs = reinterpret_cast<float*>(ws + lay.xs);
-    float* xt = reinterpret_cast<float*>(ws + lay.xt);
+    // conv1's output feeds only the second Snake of the pair, whose tensor-core FIRs read it as IEEE half:
+    // in the 16-bit modes it is written once, as half, by the conv's epilogue (no fp32 round trip)
+    void* xt = ws + lay.xt;
+    const int xd = od == SVC_F32 ? SVC_F32 : SVC_F16;
     float* y = reinterpret_cast<float*>(ws + lay.y);
     float* nxt = reinterpret_cast<float*>(ws + lay.nxt);
     void* act = ws + lay.act;
@@ -368,14 +371,18 @@ extern "C" int svc_bigvgan_forward(const svc_bigvgan_weights* w, const float* me
             for (int l = 0; l < w->n_dil; ++l) {
                 const svc_amp_pair& pr = st.pairs[j][l];
                 RUN(svc_snake_aa(src, SVC_F32, act, od, pr.a1, pr.inv_b1, B, static_cast<int>(L), O, w->precise, stream));
-                RUN(voc_conv(pr.c1, od, act, B, L, O, nullptr, 1.0f, 0, xt, nullptr, stream));
-                RUN(svc_snake_aa(xt, SVC_F32, act, od, pr.a2, pr.inv_b2, B, static_cast<int>(L), O, w->precise, stream));
+                if (xd == SVC_F32) {
+                    RUN(voc_conv(pr.c1, od, act, B, L, O, nullptr, 1.0f, 0, static_cast<float*>(xt), nullptr, od, stream));
+                } else {
+                    RUN(voc_conv(pr.c1, od, act, B, L, O, nullptr, 1.0f, 0, nullptr, xt, xd, stream));
+                }
+                RUN(svc_snake_aa(xt, xd, act, od, pr.a2, pr.inv_b2, B, static_cast<int>(L), O, w->precise, stream));
                 if (l < w->n_dil - 1) {
-                    RUN(voc_conv(pr.c2, od, act, B, L, O, src, 1.0f, 0, y, nullptr, stream));
+                    RUN(voc_conv(pr.c2, od, act, B, L, O, src, 1.0f, 0, y, nullptr, od, stream));
                     src = y;
                 } else {    // last pair: residual, then (r0 + r1 + r2) / 3 accumulated in place
                     RUN(voc_conv(pr.c2, od, act, B, L, O, src, 1.0f / nk, j > 0, nxt,
-                                 (j == nk - 1) ? nxt_op : nullptr, stream));
+                                 (j == nk - 1) ? nxt_op : nullptr, od, stream));
                 }
             }
         }

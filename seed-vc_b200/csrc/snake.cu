@@ -12,6 +12,8 @@
 // shared memory with coalesced loads; lanes map to channels, so global and shared accesses
 // are contiguous and conflict-free (row stride CT+1 spreads the time-chunks of narrow tiles
 // over the banks).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace svc {
@@ -263,6 +265,250 @@ __global__ void __launch_bounds__(256) snake_aa2_kernel(const TI* __restrict__ x
     }
 }
 
+// v3 (16-bit output, non-PRECISE): both FIRs on the tensor cores as banded-Toeplitz warp MMAs, so the FMA
+// pipe is left with the Snake nonlinearity only (the v2 kernel above is FMA-pipe bound at 0.41 of HBM peak).
+// Phases of the 2x signal: uo[q] = u[2q+1] = 2 sum_j h[2j] x[q+3-j], ue[q] = u[2q] = 2 sum_j h[2j+1] x[q+2-j],
+// y[n] = sum_j h[2j] uo[n-3+j] + sum_j h[2j+1] ue[n-2+j]   (j = 0..5; same maths as the header comment).
+// One warp owns 16 channels and walks along time in tiles of 8 frames.  The DATA is the A operand
+// (M = channels, K = 16 frames), the constant Toeplitz band is the B operand (K = 16 frames in, N = 8
+// frames out; 13 of the 16 K slots carry taps) and lives in registers for the whole kernel:
+//   u tile j (q in [N0-3+8j, +8)), both phases, from ONE A fragment = x frames [N0-6+8j, +16)
+//       (ldmatrix.trans from the fp16 (frames, channels) smem tile);
+//   Snake in fp32 on the accumulator fragment; the m16n8 accumulator layout IS the A-fragment layout, so
+//       two consecutive u tiles pack (cvt.f16x2) straight into the A operand of the down-FIR MMA;
+//   y tile (n in [N0+8t, +8)) = uo tiles (t, t+1) x Bd_o + ue tiles (t, t+1) x Bd_e.
+// The taps are split hi + lo in fp16 (two MMAs per product) so the filter response is exact to 2^-22;
+// x and u enter the MMAs as fp16 (2^-11 relative; the output is rounded to a 16-bit operand anyway).
+// Sequence ends: x rows are staged replicate-clamped; u values outside [0, 2L) are replaced by u[0] /
+// u[2L-1] (post-Snake, like the reference's replicate pad of the activated signal) with warp shuffles.
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Toeplitz entry B[k][n] of the four band matrices (kind 0: up odd, 1: up even, 2: down odd, 3: down even)
+__device__ __forceinline__ float snake_band(int kind, int k, int n) {
+    int j;
+    switch (kind) {
+        case 0: j = n + 6 - k; return (j >= 0 && j <= 5) ? c_h12x2[2 * j] : 0.f;
+        case 1: j = n + 5 - k; return (j >= 0 && j <= 5) ? c_h12x2[2 * j + 1] : 0.f;
+        case 2: j = k - n; return (j >= 0 && j <= 5) ? c_h12[2 * j] : 0.f;
+        default: j = k - n - 1; return (j >= 0 && j <= 5) ? c_h12[2 * j + 1] : 0.f;
+    }
+}
+
+// packed bf16 pair -> packed IEEE half pair
+__device__ __forceinline__ uint32_t bf162_to_f162(uint32_t v) {
+    const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&v);
+    return pack_f16(__low2float(p), __high2float(p));
+}
+
+template <typename TI, typename TO, int CT, int NS, int SPAN, bool SPLIT>
+__global__ void __launch_bounds__(32 * ((CT + 15) / 16) * NS)
+snake_mma_kernel(const TI* __restrict__ x, TO* __restrict__ out, const float* __restrict__ a_p,
+                 const float* __restrict__ invb_p, int L, int C) {
+    constexpr int MT = (CT + 15) / 16;          // 16-channel MMA row tiles per block
+    constexpr int CTP = MT * 16;                // staged channels (zero beyond CT)
+    constexpr int NTHR = 32 * MT * NS;
+    constexpr int TL = NS * SPAN;               // output frames per block
+    constexpr int XROWS = TL + 16;              // x frames l0-6 .. l0+TL+9
+    constexpr int XSTR = CTP * 2 + 16;          // bytes; +16 keeps the 8 ldmatrix rows on distinct banks
+    constexpr int OSTR = 48;                    // per-warp output staging: 8 frames x 32 B, conflict-free stride
+    extern __shared__ __align__(16) unsigned char sm3[];
+    unsigned char* xs = sm3;
+    unsigned char* os = sm3 + XROWS * XSTR;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CT;
+    const int l0 = blockIdx.x * TL;
+    const TI* xb = x + static_cast<long long>(b) * L * C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = warp % MT, ns = warp / MT;
+    const int g = lane >> 2, t = lane & 3;
+    const int N0 = l0 + ns * SPAN;
+    float a_l, ib_l, a_h, ib_h;
+    uint32_t bh[4][2], bl[4][2];
+    // per-thread constants; called between the first batch of tile loads and its use, so the arithmetic and the
+    // parameter loads overlap the DRAM round trip
+    auto setup = [&]() {
+        const int cl = c0 + mt * 16 + g, ch = cl + 8;
+        const bool vl = mt * 16 + g < CT && cl < C, vh = mt * 16 + g + 8 < CT && ch < C;
+        a_l = vl ? __ldg(a_p + cl) : 0.f, ib_l = vl ? __ldg(invb_p + cl) : 0.f;
+        a_h = vh ? __ldg(a_p + ch) : 0.f, ib_h = vh ? __ldg(invb_p + ch) : 0.f;
+        // constant band fragments: b0 = B[2t..2t+1][g], b1 = B[2t+8..2t+9][g]; hi / lo halves of every tap
+#pragma unroll
+        for (int kind = 0; kind < 4; ++kind)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float v0 = snake_band(kind, 2 * t + 8 * r, g), v1 = snake_band(kind, 2 * t + 8 * r + 1, g);
+                const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                bh[kind][r] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+                bl[kind][r] = pack_f16(v0 - __half2float(h0), v1 - __half2float(h1));
+            }
+    };
+    if constexpr (sizeof(TI) == 4) {
+        // stage: global fp32 (frames, C) -> fp16 (frames, CTP), rows clamped to the sequence.  Every thread owns one
+        // 4-channel column chunk; loads are issued in batches (the whole tile in two rounds of latency)
+        constexpr int V4 = CTP / 4, RPI = NTHR / V4, NIT = (XROWS + RPI - 1) / RPI;
+        constexpr int BATCH = NIT <= 18 ? (NIT + 1) / 2 : 8;
+        static_assert(NTHR % V4 == 0, "tile shape");
+        const int c4 = (threadIdx.x % V4) * 4, rb = threadIdx.x / V4;
+        const bool cv = c4 < CT && c0 + c4 < C;
+        const TI* xc = xb + c0 + c4;
+#pragma unroll
+        for (int i0 = 0; i0 < NIT; i0 += BATCH) {
+            float4 v[BATCH];
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+                const int r = rb + (i0 + k) * RPI;
+                const int l = min(max(l0 - 6 + r, 0), L - 1);
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i0 + k < NIT && r < XROWS && cv) v[k] = __ldg(reinterpret_cast<const float4*>(xc + static_cast<long long>(l) * C));
+            }
+            if (i0 == 0) setup();
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+                const int r = rb + (i0 + k) * RPI;
+                if (i0 + k < NIT && r < XROWS)
+                    *reinterpret_cast<uint2*>(xs + r * XSTR + c4 * 2) = make_uint2(pack_f16(v[k].x, v[k].y), pack_f16(v[k].z, v[k].w));
+            }
+        }
+    } else {
+        // 16-bit input: 8-channel (16-byte) chunks, the whole tile in flight at once; a half input is copied as it is
+        constexpr int V8 = CTP / 8, RPI = NTHR / V8, NIT = (XROWS + RPI - 1) / RPI;
+        constexpr int BATCH = NIT <= 10 ? NIT : (NIT + 1) / 2;
+        static_assert(NTHR % V8 == 0, "tile shape");
+        const int c8 = (threadIdx.x % V8) * 8, rb = threadIdx.x / V8;
+        const bool cv = c8 < CT && c0 + c8 < C;
+        const TI* xc = xb + c0 + c8;
+#pragma unroll
+        for (int i0 = 0; i0 < NIT; i0 += BATCH) {
+            uint4 v[BATCH];
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+                const int r = rb + (i0 + k) * RPI;
+                const int l = min(max(l0 - 6 + r, 0), L - 1);
+                v[k] = make_uint4(0u, 0u, 0u, 0u);
+                if (i0 + k < NIT && r < XROWS && cv) v[k] = __ldg(reinterpret_cast<const uint4*>(xc + static_cast<long long>(l) * C));
+            }
+            if (i0 == 0) setup();
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+                const int r = rb + (i0 + k) * RPI;
+                if constexpr (std::is_same<TI, __nv_bfloat16>::value) {
+                    v[k].x = bf162_to_f162(v[k].x); v[k].y = bf162_to_f162(v[k].y);
+                    v[k].z = bf162_to_f162(v[k].z); v[k].w = bf162_to_f162(v[k].w);
+                }
+                if (i0 + k < NIT && r < XROWS) *reinterpret_cast<uint4*>(xs + r * XSTR + c8 * 2) = v[k];
+            }
+        }
+    }
+    __syncthreads();
+    if (N0 >= L) return;                        // no block-level barrier below this line
+    // ldmatrix.x4.trans row address of this lane: matrices (ch 0-7 | 8-15) x (frames 0-7 | 8-15)
+    const int lm = lane >> 3, lr = lane & 7;
+    uint32_t xaddr = smem_u32(xs) + (ns * SPAN + lr + (lm >> 1) * 8) * XSTR + (mt * 16 + (lm & 1) * 8) * 2;
+    // per-warp output staging, double buffered: stmatrix.x2.trans rows in, one 8-byte chunk per lane out
+    const uint32_t obase = smem_u32(os) + warp * (2 * 8 * OSTR);
+    const uint32_t oaddr_st = obase + (lane & 7) * OSTR + ((lane >> 3) & 1) * 16;
+    const uint32_t oaddr_ld = obase + g * OSTR + t * 8;
+    // copy-out: lane = (frame g, channels 4t .. 4t+3)
+    TO* op = out + (static_cast<long long>(b) * L + N0 + g) * C + c0 + mt * 16 + t * 4;
+    const long long ostep = 8LL * C;
+    const bool ovalid = mt * 16 + t * 4 < CT && c0 + mt * 16 + t * 4 < C;
+
+    float vLl = 0.f, vLh = 0.f;                 // u[2L-1] of this thread's two channels, once seen
+    uint32_t po[2], pe[2];                      // previous u tile, packed: [0] = channel g, [1] = channel g+8
+
+    // one u tile (both phases) from the A fragment at xaddr; EDGE: a sequence end may lie inside (qs = q of column 0)
+    auto u_tile = [&](auto edge, int qs, uint32_t (&no)[2], uint32_t (&ne)[2]) {
+        constexpr bool EDGE = decltype(edge)::value;
+        uint32_t xa[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(xa[0]), "=r"(xa[1]), "=r"(xa[2]), "=r"(xa[3])
+                     : "r"(xaddr));
+        xaddr += 8 * XSTR;
+        float uo[4] = {0.f, 0.f, 0.f, 0.f}, ue[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816(uo, xa, bh[0][0], bh[0][1]);
+        mma16816(ue, xa, bh[1][0], bh[1][1]);
+        if constexpr (SPLIT) {
+            mma16816(uo, xa, bl[0][0], bl[0][1]);
+            mma16816(ue, xa, bl[1][0], bl[1][1]);
+        }
+        uo[0] = snake_fn<false>(uo[0], a_l, ib_l); uo[1] = snake_fn<false>(uo[1], a_l, ib_l);
+        uo[2] = snake_fn<false>(uo[2], a_h, ib_h); uo[3] = snake_fn<false>(uo[3], a_h, ib_h);
+        ue[0] = snake_fn<false>(ue[0], a_l, ib_l); ue[1] = snake_fn<false>(ue[1], a_l, ib_l);
+        ue[2] = snake_fn<false>(ue[2], a_h, ib_h); ue[3] = snake_fn<false>(ue[3], a_h, ib_h);
+        if constexpr (EDGE) {
+            if (qs < 0 || qs + 8 >= L) {        // warp-uniform: frame 0 / frame L-1 or beyond inside this tile
+                if (qs < 0) {                   // q < 0 -> u[0] = ue[q = 0], column -qs
+                    const int n0c = -qs, src = (lane & ~3) | (n0c >> 1);
+                    const float sl = __shfl_sync(0xffffffffu, (n0c & 1) ? ue[1] : ue[0], src);
+                    const float sh = __shfl_sync(0xffffffffu, (n0c & 1) ? ue[3] : ue[2], src);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        if (qs + 2 * t + e < 0) { uo[e] = sl; ue[e] = sl; uo[2 + e] = sh; ue[2 + e] = sh; }
+                }
+                if (qs <= L - 1 && L - 1 < qs + 8) {   // this tile holds q = L-1: u[2L-1] = uo[L-1]
+                    const int nLc = L - 1 - qs, src = (lane & ~3) | (nLc >> 1);
+                    vLl = __shfl_sync(0xffffffffu, (nLc & 1) ? uo[1] : uo[0], src);
+                    vLh = __shfl_sync(0xffffffffu, (nLc & 1) ? uo[3] : uo[2], src);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (qs + 2 * t + e >= L) { uo[e] = vLl; ue[e] = vLl; uo[2 + e] = vLh; ue[2 + e] = vLh; }
+            }
+        }
+        no[0] = pack_f16(uo[0], uo[1]); no[1] = pack_f16(uo[2], uo[3]);
+        ne[0] = pack_f16(ue[0], ue[1]); ne[1] = pack_f16(ue[2], ue[3]);
+    };
+    // y tile from the previous and the new u tile; (channel, frame) fragment -> (frame, channel) rows through the
+    // warp's staging tile, then 8-byte stores: one full 32-byte sector per frame and warp
+    auto y_tile = [&](const uint32_t (&no)[2], const uint32_t (&ne)[2], int buf, bool store) {
+        const uint32_t ao[4] = {po[0], po[1], no[0], no[1]}, ae[4] = {pe[0], pe[1], ne[0], ne[1]};
+        float y[4] = {0.f, 0.f, 0.f, 0.f};
+        mma16816(y, ao, bh[2][0], bh[2][1]);
+        mma16816(y, ae, bh[3][0], bh[3][1]);
+        if constexpr (SPLIT) {
+            mma16816(y, ao, bl[2][0], bl[2][1]);
+            mma16816(y, ae, bl[3][0], bl[3][1]);
+        }
+        po[0] = no[0]; po[1] = no[1]; pe[0] = ne[0]; pe[1] = ne[1];
+        const uint32_t y0 = pack2<TO>(y[0], y[1]), y1 = pack2<TO>(y[2], y[3]);
+        asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1,%2};" ::"r"(oaddr_st + buf * (8 * OSTR)),
+                     "r"(y0), "r"(y1)
+                     : "memory");
+        __syncwarp();
+        uint2 v;
+        asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(oaddr_ld + buf * (8 * OSTR)) : "memory");
+        if (store) *reinterpret_cast<uint2*>(op) = v;
+        op += ostep;
+    };
+
+    // interior span: every u tile of the span lies inside [0, L) and every output frame exists
+    if (N0 >= 3 && N0 + SPAN + 5 <= L) {
+        u_tile(std::false_type{}, 0, po, pe);
+#pragma unroll 4
+        for (int tt = 0; tt < SPAN / 8; ++tt) {
+            uint32_t no[2], ne[2];
+            u_tile(std::false_type{}, 0, no, ne);
+            y_tile(no, ne, tt & 1, ovalid);
+        }
+    } else {
+        int qs = N0 - 3;
+        u_tile(std::true_type{}, qs, po, pe);
+        for (int tt = 0; tt < SPAN / 8; ++tt) {
+            const int n0 = N0 + 8 * tt;
+            if (n0 >= L) break;
+            qs += 8;
+            uint32_t no[2], ne[2];
+            u_tile(std::true_type{}, qs, no, ne);
+            y_tile(no, ne, tt & 1, ovalid && n0 + g < L);
+        }
+    }
+}
+
 constexpr int kPostTL = 128;    // output samples per block of snake_conv_post_kernel
 
 // activation_post + conv_post (C -> 1, k taps, zero padding) + clamp / tanh.
@@ -363,6 +609,33 @@ static void launch_snake2(const TI* xi, TO* o, const float* a, const float* inv_
     snake_aa2_kernel<TI, TO, CT, LPT, PRECISE><<<grid, 256, SMEM, st>>>(xi, o, a, inv_b, L, C);
 }
 
+#ifndef SVC_SNAKE_NS        // time spans per block / frames per span of the 64-channel tile (experiment builds override)
+#define SVC_SNAKE_NS 2
+#define SVC_SNAKE_SPAN 128
+#endif
+#ifdef SVC_SNAKE_NOSPLIT
+constexpr bool kSnakeSplitTaps = false;     // experiment build: single fp16 tap (filter response exact to 2^-11 only)
+#else
+constexpr bool kSnakeSplitTaps = true;
+#endif
+
+template <typename TI, typename TO, int CT, int NS, int SPAN>
+static int launch_snake3(const TI* xi, TO* o, const float* a, const float* inv_b, int B, int L, int C,
+                         cudaStream_t st) {
+    constexpr int MT = (CT + 15) / 16, TL = NS * SPAN;
+    constexpr int SMEM = (TL + 16) * (MT * 32 + 16) + MT * NS * 2 * 8 * 48;
+    auto kern = snake_mma_kernel<TI, TO, CT, NS, SPAN, kSnakeSplitTaps>;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        attr = true;
+    }
+    dim3 grid((L + TL - 1) / TL, (C + CT - 1) / CT, B);
+    kern<<<grid, 32 * MT * NS, SMEM, st>>>(xi, o, a, inv_b, L, C);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
 template <typename TI, typename TO, bool PRECISE>
 static int launch_snake(const void* x, void* out, const float* a, const float* inv_b, int B, int L,
                         int C, cudaStream_t st) {
@@ -370,6 +643,16 @@ static int launch_snake(const void* x, void* out, const float* a, const float* i
     TO* o = static_cast<TO*>(out);
     const bool al = reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 8 == 0 &&
                     reinterpret_cast<uintptr_t>(a) % 8 == 0 && reinterpret_cast<uintptr_t>(inv_b) % 8 == 0;
+    if constexpr (!PRECISE && sizeof(TO) == 2) {
+        // 16-bit operand output: FIRs on the tensor cores (snake_mma_kernel)
+        if (al && C % 8 == 0) {
+            if (C % 64 == 0) return launch_snake3<TI, TO, 64, SVC_SNAKE_NS, SVC_SNAKE_SPAN>(xi, o, a, inv_b, B, L, C, st);
+            if (C % 48 == 0) return launch_snake3<TI, TO, 48, 2, 128>(xi, o, a, inv_b, B, L, C, st);
+            if (C % 32 == 0) return launch_snake3<TI, TO, 32, 4, 64>(xi, o, a, inv_b, B, L, C, st);
+            if (C % 24 == 0) return launch_snake3<TI, TO, 24, 4, 64>(xi, o, a, inv_b, B, L, C, st);
+            if (C % 16 == 0) return launch_snake3<TI, TO, 16, 8, 32>(xi, o, a, inv_b, B, L, C, st);
+        }
+    }
     if (al && C % 64 == 0) {
         launch_snake2<TI, TO, 64, 16, PRECISE>(xi, o, a, inv_b, B, L, C, st);
     } else if (al && C % 32 == 0) {
@@ -406,15 +689,19 @@ extern "C" int svc_snake_aa(const void* x, int x_dtype, void* out, int out_dtype
         return SVC_ERR_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define SNAKE_DISPATCH(TI, TO)                                                         \
-    return precise ? launch_snake<TI, TO, true>(x, out, a, inv_b, B, L, C, st)         \
-                   : launch_snake<TI, TO, false>(x, out, a, inv_b, B, L, C, st)
+#define SNAKE_DISPATCH(TI, TO) return launch_snake<TI, TO, false>(x, out, a, inv_b, B, L, C, st)
+    if (precise) {   // libm sinf: the fp32 parity mode only
+        if (x_dtype == SVC_F32 && out_dtype == SVC_F32) return launch_snake<float, float, true>(x, out, a, inv_b, B, L, C, st);
+        svc_set_error("svc_snake_aa: precise = 1 needs fp32 input and output");
+        return SVC_ERR_UNSUPPORTED;
+    }
     if (x_dtype == SVC_F32 && out_dtype == SVC_F32) { SNAKE_DISPATCH(float, float); }
     if (x_dtype == SVC_F32 && out_dtype == SVC_BF16) { SNAKE_DISPATCH(float, __nv_bfloat16); }
     if (x_dtype == SVC_BF16 && out_dtype == SVC_BF16) { SNAKE_DISPATCH(__nv_bfloat16, __nv_bfloat16); }
     if (x_dtype == SVC_BF16 && out_dtype == SVC_F32) { SNAKE_DISPATCH(__nv_bfloat16, float); }
     if (x_dtype == SVC_F32 && out_dtype == SVC_F16) { SNAKE_DISPATCH(float, __half); }
     if (x_dtype == SVC_F16 && out_dtype == SVC_F16) { SNAKE_DISPATCH(__half, __half); }
+    if (x_dtype == SVC_F16 && out_dtype == SVC_BF16) { SNAKE_DISPATCH(__half, __nv_bfloat16); }
     if (x_dtype == SVC_F16 && out_dtype == SVC_F32) { SNAKE_DISPATCH(__half, float); }
 #undef SNAKE_DISPATCH
     svc_set_error("svc_snake_aa: unsupported dtype");
