@@ -61,6 +61,9 @@ if "gemm" in what:
         ("merge K80 N512 +res->f32", [C], D, dict(res=True), "f32"),
         ("wn_in 5xK512 N1024 gate->bf16", [Dw] * 5, 2 * Dw, dict(act=_lib.ACT_TANH_SIG_PAIR), "op"),
         ("wn_rs K512 N512 +res->f32+bf16", [Dw], Dw, dict(res=True), "both"),
+        ("wn_rsB K512 N512 bias+res->f32+bf16", [Dw], Dw, dict(res=True, bias=True), "both"),
+        ("w2d  K1536 N512 +res->f32+bf16", [I], D, dict(res=True), "both"),
+        ("wod  K512 N512 +res->f32+bf16", [D], D, dict(res=True), "both"),
         ("conv2 K512 N80 ->f32", [Dw], C, dict(), "f32"),
     ]
     flt = os.environ.get("KB_FILTER", "")

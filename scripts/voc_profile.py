@@ -1,11 +1,12 @@
-"""Per-launch timing of one BigVGAN forward at config-2 size (B=32, Tm=2150)."""
+"""Per-launch timing of one BigVGAN forward at config-2 size (B=32, Tm=2150).  usage: voc_profile.py [bf16|fp16]"""
 import os, sys, torch, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import seedvc_b200
 from seedvc_b200 import configs, synth
 from seedvc_b200.bigvgan import BigVGAN
 from seedvc_b200 import ops as ops_mod
-voc = BigVGAN(configs.bigvgan_h()).to("cuda")
+mode = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+voc = BigVGAN(configs.bigvgan_h(), mode=mode).to("cuda")
 mel = synth.synth_mel(32, 80, 2150).to("cuda")
 voc(mel); torch.cuda.synchronize()
 ops = voc._prepare()["ops"]

@@ -144,6 +144,9 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 // control dependency costs more than the 72 instructions it removes; polynomial exp2 on every 2nd / 4th pair
 // 585 / 681 (every 3rd stays best); the packed ex2.approx.bf16x2 / f16x2 forms compile to two MUFU.EX2
 // instructions per pair (scripts/ubench/mufu2.cu), so they cannot lift the XU bound either.
+// Scalar forms of the packed f32x2 arithmetic (an FFMA2 costs 3 FMA-pipe cycles, two FFMAs with an immediate operand
+// 2: scripts/ubench/pipes.cu) lose as well - 829 (s * log2e - m), 793 (+ row-sum adds), 833 (polynomial only), 755 (all)
+// against 868: the softmax warps are short of ISSUE slots, not of FMA-pipe cycles.
 // F16: operands (Q, K, V, the P tile and the output) are IEEE half instead of bf16 - same instruction, the
 // format bits of the instruction descriptor and the conversions differ.
 template <bool F16>

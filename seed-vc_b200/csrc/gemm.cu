@@ -51,6 +51,8 @@ struct alignas(64) TcParams {
     int direct;                // 1: row-layout epilogue writes the swizzled TMA tile directly (no transpose)
     int res_rows;              // direct: residual read in the row layout (one 128 B line per thread)
     int dual;                  // direct: fp32 tile -> out_f32 (omap) AND bf16 tile -> out_op (omap2)
+    int res_tma;               // dual: the residual item is TMA-loaded into the staging tile (rmap), not read by LSU
+    CUtensorMap rmap;          // (N_out, T, B) view of the residual, same box / swizzle as omap
     CUtensorMap omap2;
     CUtensorMap omap;          // (N_out, T, B) view of the output, box {32, 32, 1}; swizzled when direct
     EpiParams epi;
@@ -79,6 +81,16 @@ __device__ long long g_gemm_trace[2][128][8];   // [0]: epilogue warp 2 lane 0 p
 constexpr int kEpiWarps = 8;             // two epilogue groups of 4 warps (one per TMEM buffer)
 constexpr int kTcThreads = 64 + kEpiWarps * 32;    // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kStageRowF = 32;           // fp32 row of the per-warp transpose buffer (XOR-swizzled)
+// two-output epilogue (EPI 5): per warp two fp32 item tiles (the residual of item k+1 is TMA-loaded into one while
+// item k is finished in the other) + one 16-bit tile
+constexpr int kDualWarpBytes = 2 * 4096 + 2048;
+constexpr int kDualOpOff = 2 * 4096;
+// deepest operand ring that fits next to the two-output epilogue's staging tiles
+constexpr int epi5_stages(int bn, int stages) {
+    const int stage_bytes = (BM + bn) * BK * 2;
+    const int fit = (232448 - 8 * kDualWarpBytes - 512 - 1024) / stage_bytes;
+    return fit < stages - 1 ? fit : stages - 1;
+}
 
 template <int BN, int STAGES, int EPW = 4096>
 struct TcSmem {
@@ -89,7 +101,7 @@ struct TcSmem {
     static constexpr int EPI_WARP_BYTES = EPW;       // per epilogue warp: fp32 tile (+ bf16 tile when dual)
     static constexpr int EPI_BYTES = kEpiWarps * EPW;
     static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+    static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;  // + barriers + alignment slack
     static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
@@ -498,13 +510,16 @@ __device__ __forceinline__ void res_prefetch_rows(const EpiParams& e, int c0, in
 // branches.  The kernel picks EK once (epi_kind) and runs the item loop specialised for it:
 //   0 generic (every check at run time)      1 no vector operand; act = none or (pair) SwiGLU
 //   2 interleaved-pair RoPE, nothing else     3 bias only (+ row-layout residual in the two-output epilogue)
-//   4 per-batch bias + tanh * sigmoid pair (WaveNet in-layers)
-constexpr int EK_GENERIC = 0, EK_PLAIN = 1, EK_ROPE = 2, EK_BIAS = 3, EK_ROWBIAS_TS = 4;
+//   4 per-batch bias + tanh * sigmoid pair (WaveNet in-layers)   5 residual only, two outputs (w2 / wo with an operand copy)
+constexpr int EK_GENERIC = 0, EK_PLAIN = 1, EK_ROPE = 2, EK_BIAS = 3, EK_ROWBIAS_TS = 4, EK_RES = 5;
 
+// rbar / ridx: two-output epilogue with a TMA-loaded residual - the item's residual tile arrives in fp32 staging
+// buffer (ridx & 1) under mbarrier rbar[ridx & 1]; the finished fp32 tile is written over it and stored from there.
 template <bool PAIR, int EK, bool DUAL>
 __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* stage, int lane, int b,
                                                      int t_base, int n0_acc, float (&v)[PAIR ? 64 : 32],
-                                                     const float4 (&rr)[8]) {
+                                                     const float4 (&rr)[8], uint64_t* rbar = nullptr,
+                                                     uint32_t ridx = 0) {
     const EpiParams& e = p.epi;
     constexpr int NA = PAIR ? 64 : 32;
     constexpr bool G = EK == EK_GENERIC;
@@ -512,7 +527,9 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     const bool has_bias = G ? e.bias != nullptr : EK == EK_BIAS;
     const bool has_rowbias = G ? e.rowbias != nullptr : EK == EK_ROWBIAS_TS;
     const bool has_gate = G ? e.gate != nullptr : false;
-    const bool has_res = G ? p.res_rows != 0 : (EK == EK_BIAS && DUAL && p.res_rows != 0);
+    const bool has_res = G ? p.res_rows != 0 : EK == EK_RES ? true : (EK == EK_BIAS && DUAL && p.res_rows != 0);
+    const bool res_tma = DUAL && p.res_tma;                 // warp-uniform
+    uint8_t* const fbuf = reinterpret_cast<uint8_t*>(stage) + ((DUAL && res_tma) ? (ridx & 1) * 4096 : 0);
     const bool has_alpha = G ? e.alpha != 1.0f : false;
     const int act = G ? e.act
                       : EK == EK_ROPE ? SVC_ACT_ROPE
@@ -566,9 +583,20 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
             }
     }
     if (!PAIR && has_res) {
+        if (res_tma) {
+            mbar_wait_warp(&rbar[ridx & 1], (ridx >> 1) & 1);
+            const uint8_t* row = fbuf + lane * 128;
+            const int sw = lane & 7;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            v[4 * q] += rr[q].x, v[4 * q + 1] += rr[q].y, v[4 * q + 2] += rr[q].z, v[4 * q + 3] += rr[q].w;
+            for (int q = 0; q < 8; ++q) {
+                const float4 r4 = *reinterpret_cast<const float4*>(row + ((q ^ sw) << 4));
+                v[4 * q] += r4.x, v[4 * q + 1] += r4.y, v[4 * q + 2] += r4.z, v[4 * q + 3] += r4.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                v[4 * q] += rr[q].x, v[4 * q + 1] += rr[q].y, v[4 * q + 2] += rr[q].z, v[4 * q + 3] += rr[q].w;
+        }
     }
     if (has_alpha) {
 #pragma unroll
@@ -579,7 +607,7 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     __syncwarp();
     uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
     if (p.store_mode == 1 || DUAL) {
-        uint8_t* row = sb + (DUAL ? 4096 : 0) + lane * 64;
+        uint8_t* row = sb + (DUAL ? kDualOpOff : 0) + lane * 64;
         const int sw = (lane >> 1) & 3;
         if (e.op_is_f16) {         // warp-uniform: one conversion flavour per launch
 #pragma unroll
@@ -596,7 +624,7 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
         }
     }
     if (p.store_mode != 1) {
-        uint8_t* row = sb + lane * 128;
+        uint8_t* row = fbuf + lane * 128;
         const int sw = lane & 7;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -606,9 +634,9 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-        if (p.store_mode == 2) tma_reduce_add_3d(&p.omap, stage, c0, t_base, b);
-        else tma_store_3d(&p.omap, stage, c0, t_base, b);
-        if (DUAL) tma_store_3d(&p.omap2, sb + 4096, c0, t_base, b);
+        if (p.store_mode == 2) tma_reduce_add_3d(&p.omap, fbuf, c0, t_base, b);
+        else tma_store_3d(&p.omap, fbuf, c0, t_base, b);
+        if (DUAL) tma_store_3d(&p.omap2, sb + kDualOpOff, c0, t_base, b);
         bulk_commit();
     }
 }
@@ -624,6 +652,7 @@ __device__ __forceinline__ int epi_kind(const TcParams& p, bool pair, bool dual)
         if (!pair && e.act == SVC_ACT_ROPE) return EK_ROPE;
     }
     if (b && !rb && !pair && e.act == SVC_ACT_NONE && (dual || !rs)) return EK_BIAS;
+    if (!b && !rb && rs && dual && !pair && e.act == SVC_ACT_NONE) return EK_RES;
     if (rb && !b && !rs && pair && e.act == SVC_ACT_TANH_SIG_PAIR) return EK_ROWBIAS_TS;
     return EK_GENERIC;
 }
@@ -636,7 +665,7 @@ __device__ __forceinline__ int epi_kind(const TcParams& p, bool pair, bool dual)
 // registers and code small.
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
-    using S = TcSmem<BN, STAGES, EPI == 5 ? 6144 : 4096>;
+    using S = TcSmem<BN, STAGES, EPI == 5 ? kDualWarpBytes : 4096>;
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
     constexpr int kTmemCols = 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;   // power of two
     extern __shared__ uint8_t smem_raw[];
@@ -646,7 +675,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* res_bar = tmem_empty_bar + 2;           // [kEpiWarps][2]: TMA-loaded residual items (EPI 5)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -666,6 +696,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             mbar_init(&tmem_full_bar[a], 1);
             mbar_init(&tmem_empty_bar[a], kEpiWarps / 2);
         }
+        for (int a = 0; a < 2 * kEpiWarps; ++a) mbar_init(&res_bar[a], 1);
+        if (EPI == 5 && p.res_tma) tma_prefetch_desc(&p.rmap);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -820,8 +852,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             epi_prefetch(p.epi, g_cur, lane, cur.b, cur.t_base, p.T, rr_cur);
         if (rope_direct && cur.valid && cur.n0c < p.epi.rope_cols)
             rope_prefetch_rows(p.epi, cur.n0c, lane, cur.t_base, rr_cur);
-        const bool res_direct = EK == EK_GENERIC ? (direct && !pair && p.res_rows)
-                                                 : (EK == EK_BIAS && EPI == 5 && p.res_rows);
+        const bool res_any = EK == EK_GENERIC ? (direct && !pair && p.res_rows)
+                                              : ((EK == EK_BIAS || EK == EK_RES) && EPI == 5 && p.res_rows);
+        const bool res_tma = EPI == 5 && res_any && p.res_tma;      // residual item through TMA into the staging tile
+        const bool res_direct = res_any && !res_tma;                // ... or one 128-byte line per thread by LSU
+        uint64_t* const rbar = res_bar + 2 * ew;
+        uint32_t r_issued = 0, r_used = 0;                          // processed items only (t_base < T)
+        auto res_issue = [&](const Item& x) {                       // lane 0
+            mbar_expect_tx(&rbar[r_issued & 1], 4096);
+            tma_load_3d(reinterpret_cast<uint8_t*>(stage_buf) + (r_issued & 1) * 4096, &p.rmap, &rbar[r_issued & 1],
+                        x.n0c, x.t_base, x.b);
+        };
+        if (res_tma && cur.valid && cur.t_base < p.T) {
+            if (lane == 0) res_issue(cur);
+            ++r_issued;
+        }
         if (res_direct && cur.valid) res_prefetch_rows(p.epi, cur.n0c, lane, cur.b, cur.t_base, p.T, rr_cur);
         int tr_i = 0;
         const bool tr_on = (warp == 2 && lane == 0);
@@ -850,6 +895,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 }
             }
             if (res_direct && nxt.valid) res_prefetch_rows(p.epi, nxt.n0c, lane, nxt.b, nxt.t_base, p.T, rr_nxt);
+            if (res_tma && nxt.valid && nxt.t_base < p.T) {
+                if (lane == 0) {
+                    bulk_wait_read0();          // the stores of the item before this one have read the target buffer
+                    res_issue(nxt);
+                }
+                ++r_issued;
+            }
             if (tr_on) GTRACE(0, tr_i, 1);
             tc_wait_ld();
             if (tr_on) GTRACE(0, tr_i, 2);
@@ -875,9 +927,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if constexpr (direct) epilogue_item_direct<false, EK, EPI == 5>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                    if constexpr (direct) epilogue_item_direct<false, EK, EPI == 5>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur, rbar, r_used);
                     else epilogue_item_tma<false>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
                 }
+                ++r_used;
             }
             if (tr_on) GTRACE(0, tr_i, 3);
             ++tr_i;
@@ -898,6 +951,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             if constexpr (EPI == 3 || EPI == 5) run_items(std::integral_constant<int, EK_BIAS>{});
         } else if (EPI == 4 && ek == EK_ROWBIAS_TS) {
             if constexpr (EPI == 4) run_items(std::integral_constant<int, EK_ROWBIAS_TS>{});
+        } else if (EPI == 5 && ek == EK_RES) {
+            if constexpr (EPI == 5) run_items(std::integral_constant<int, EK_RES>{});
         } else {
             run_items(ek0{});
         }
@@ -1052,7 +1107,7 @@ static bool encode_out_map(CUtensorMap* map, const void* ptr, bool f32, int n_ou
 
 template <int BN, int STAGES, int EPI>
 static int launch_tc_epi(const TcParams& p, int m_tiles, cudaStream_t stream) {
-    using S = TcSmem<BN, STAGES, EPI == 5 ? 6144 : 4096>;
+    using S = TcSmem<BN, STAGES, EPI == 5 ? kDualWarpBytes : 4096>;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI>,
@@ -1074,7 +1129,7 @@ static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
         if (pair) return p.direct ? launch_tc_epi<BN, STAGES, 4>(p, m_tiles, stream)
                                   : launch_tc_epi<BN, STAGES, 2>(p, m_tiles, stream);
     }
-    if (p.dual) return launch_tc_epi<BN, (BN == 256 ? 3 : STAGES - 1), 5>(p, m_tiles, stream);
+    if (p.dual) return launch_tc_epi<BN, epi5_stages(BN, STAGES), 5>(p, m_tiles, stream);
     return p.direct ? launch_tc_epi<BN, STAGES, 3>(p, m_tiles, stream)
                     : launch_tc_epi<BN, STAGES, 1>(p, m_tiles, stream);
 }
@@ -1197,6 +1252,7 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
     // ---- TMA-store epilogue when the output pattern allows it ------------------------------
     static const int no_tma_store = svc_env_flag("SVC_NO_TMA_STORE") ? 1 : 0;
     static const int no_direct = svc_env_flag("SVC_NO_DIRECT") ? 1 : 0;
+    static const int no_res_tma = svc_env_flag("SVC_NO_RES_TMA") ? 1 : 0;
     p.store_mode = 0;
     // row-layout epilogue (no transpose); RoPE needs the pair-major table
     p.direct = !no_direct && d.N % 4 == 0 &&
@@ -1229,6 +1285,9 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
             p.store_mode = d.accumulate ? 2 : 3;
             p.res_rows = d.res != nullptr;
             p.dual = d.out_op != nullptr;
+            // residual items by TMA (same box and swizzle as the fp32 output tile they are finished in)
+            p.res_tma = d.res != nullptr && !no_res_tma &&
+                        encode_out_map(&p.rmap, d.res, true, p.epi.N_out, d.T, d.res_rstride, d.B, d.res_bstride, true);
         }
     }
     if (BN < 64 && pair_act) p.store_mode = 0;
