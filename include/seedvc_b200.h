@@ -103,7 +103,21 @@ typedef struct svc_gemm_desc {
     /* element type of out_op when it differs from the operands': 0 = same as dtype, else 1 + SVC_BF16 / SVC_F16
        (a bf16 GEMM may write an fp16 operand copy and vice versa; fp32 GEMMs write fp32). */
     int out_op_dtype_p1;
+    /* RMS normalisation folded into the GEMMs around it (AdaptiveLayerNorm / RMSNorm, diffusion_transformer.py:30-48):
+       y = x * rsqrt(mean(x^2) + eps) * g + a  feeding a Linear W  ==  rsqrt(..) * (x (W * g)^T) + a W^T, so the
+       caller folds g into the weight columns and a W^T into `bias`, the GEMM that PRODUCES x reports the row sums of
+       squares and the GEMM that CONSUMES x scales its accumulator rows.
+       row_ss_out: (B*T, SVC_SS_SLOTS) fp32, contiguous, zeroed once by the caller.  Two-output tensor-core calls
+         (out_f32 + out_op) write, per output row, the sum of squares of the final fp32 values of every N tile into
+         the leading slots (untouched slots keep their zeros).  N % 32 == 0, at most SVC_SS_SLOTS tiles.
+       row_ss_in: the same array from an earlier call: acc[r,:] *= rsqrt(sum(slots[r]) * rs_inv_dim + rs_eps) before
+         the bias.  Tensor-core calls with bias + (RoPE | SwiGLU pair) -> out_op only.
+       NULL = off.  Not available on the SIMT / fp32 path (SVC_ERR_UNSUPPORTED). */
+    float* row_ss_out;
+    const float* row_ss_in;
+    float rs_inv_dim, rs_eps;
 } svc_gemm_desc;
+#define SVC_SS_SLOTS 4
 
 int svc_gemm(const svc_gemm_desc* d, int backend, void* stream);
 
@@ -177,6 +191,12 @@ int svc_btc_to_bct(const float* in, float* out, int B, int T, int C, void* strea
 
 /* fp32 -> operand dtype, n contiguous elements */
 int svc_cast(const float* in, void* out, long long n, int out_dtype, void* stream);
+
+/* Folded RMS norm, weight side: out[s][n][k] = W[n][k] * g[k] * mul[s][k] in out_dtype, s < S (one copy per Euler
+ * step).  W fp32 (N, K) with row stride w_rstride; g [K] (RMSNorm weight) and mul [S][mul_stride] (AdaLN weight per
+ * step) may be NULL.  The matching bias a_s W^T is an ordinary fp32 svc_gemm.  See svc_gemm_desc.row_ss_in. */
+int svc_scale_cols(const float* W, long long w_rstride, const float* g, const float* mul, long long mul_stride,
+                   void* out, int out_dtype, int S, int N, int K, void* stream);
 
 /* Reflect padding halo of the WaveNet input (encodec.py:212-228 `pad1d(..., 'reflect')`):
  * buf is (B, T + 2*pad, C) in the operand dtype with the body at rows [pad, pad+len_b);

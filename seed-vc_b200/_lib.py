@@ -36,7 +36,11 @@ class GemmDesc(C.Structure):
         ("out_f32", c_vp), ("of_bstride", c_ll), ("of_rstride", c_ll),
         ("out_op", c_vp), ("oo_bstride", c_ll), ("oo_rstride", c_ll),
         ("rope_tab_t", c_vp), ("rope_ld", c_int), ("out_op_dtype_p1", c_int),
+        ("row_ss_out", c_vp), ("row_ss_in", c_vp), ("rs_inv_dim", c_float), ("rs_eps", c_float),
     ]
+
+
+SS_SLOTS = 4     # SVC_SS_SLOTS
 
 
 MAX_LAYERS, MAX_WN_LAYERS, MAX_BRANCH = 32, 16, 3
@@ -120,6 +124,7 @@ SIGNATURES = {
     "svc_bct_to_btc": [c_vp, c_vp, c_ll, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_vp],
     "svc_btc_to_bct": [c_vp, c_vp, c_int, c_int, c_int, c_vp],
     "svc_cast": [c_vp, c_vp, c_ll, c_int, c_vp],
+    "svc_scale_cols": [c_vp, c_ll, c_vp, c_vp, c_ll, c_vp, c_int, c_int, c_int, c_int, c_vp],
     "svc_reflect_halo": [c_vp, c_ll, c_ll, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp],
     "svc_timestep_embedding": [c_vp, c_vp, c_vp, c_int, c_int, c_vp],
     "svc_set_rows": [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_vp],

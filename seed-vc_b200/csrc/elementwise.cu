@@ -378,6 +378,61 @@ extern "C" int svc_cast(const float* in, void* out, long long n, int out_dtype, 
     return SVC_OK;
 }
 
+// out[s][n][k] = W[n][k] * g[k] * mul[s][k]  (folded RMS norm: the norm's per-column factors into the weight columns)
+template <typename TO>
+__global__ void __launch_bounds__(256) scale_cols_kernel(const float* __restrict__ W, long long w_rstride,
+                                                         const float* __restrict__ g, const float* __restrict__ mul,
+                                                         long long mul_stride, TO* __restrict__ out, int N, int K) {
+    const int s = blockIdx.y;
+    const long long per = static_cast<long long>(N) * K;
+    const float* ms = mul != nullptr ? mul + s * mul_stride : nullptr;
+    TO* o = out + s * per;
+    for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 4; i < per;
+         i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+        const int n = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<long long>(n) * K);
+        float4 w = __ldg(reinterpret_cast<const float4*>(W + n * w_rstride + k));
+        if (g != nullptr) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(g + k));
+            w.x *= q.x, w.y *= q.y, w.z *= q.z, w.w *= q.w;
+        }
+        if (ms != nullptr) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(ms + k));
+            w.x *= q.x, w.y *= q.y, w.z *= q.z, w.w *= q.w;
+        }
+        if constexpr (sizeof(TO) == 4) {
+            *reinterpret_cast<float4*>(o + i) = w;
+        } else {
+            uint2 q;
+            q.x = pack2<TO>(w.x, w.y);
+            q.y = pack2<TO>(w.z, w.w);
+            *reinterpret_cast<uint2*>(o + i) = q;
+        }
+    }
+}
+
+extern "C" int svc_scale_cols(const float* W, long long w_rstride, const float* g, const float* mul, long long mul_stride,
+                              void* out, int out_dtype, int S, int N, int K, void* stream) {
+    if (S < 1 || N < 1 || K < 4 || K % 4 != 0 || w_rstride % 4 != 0 || (mul != nullptr && mul_stride % 4 != 0) ||
+        reinterpret_cast<uintptr_t>(W) % 16 != 0 || reinterpret_cast<uintptr_t>(out) % 16 != 0 ||
+        (g != nullptr && reinterpret_cast<uintptr_t>(g) % 16 != 0) ||
+        (mul != nullptr && reinterpret_cast<uintptr_t>(mul) % 16 != 0)) {
+        svc_set_error("svc_scale_cols: K % 4 == 0 and 16-byte aligned pointers / strides required");
+        return SVC_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long per = static_cast<long long>(N) * K;
+    dim3 grid(static_cast<unsigned>(std::min<long long>((per / 4 + 255) / 256, kNumSMs * 8)), S);
+    if (out_dtype == SVC_F32)
+        scale_cols_kernel<float><<<grid, 256, 0, st>>>(W, w_rstride, g, mul, mul_stride, static_cast<float*>(out), N, K);
+    else if (out_dtype == SVC_F16)
+        scale_cols_kernel<__half><<<grid, 256, 0, st>>>(W, w_rstride, g, mul, mul_stride, static_cast<__half*>(out), N, K);
+    else
+        scale_cols_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(W, w_rstride, g, mul, mul_stride,
+                                                               static_cast<__nv_bfloat16*>(out), N, K);
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
+}
+
 extern "C" int svc_reflect_halo(void* buf, long long bstride, long long rstride, int B, int T, int C,
                                 int pad, const int* lens, int dtype, void* stream) {
     if (pad < 1 || T < pad + 1) {

@@ -30,6 +30,9 @@ struct EpiParams {
     int op_is_f32;
     int op_is_f16;             // 16-bit operand format: 1 = IEEE half, 0 = bf16
     int vec_ok;  // every pointer / stride involved is 16-byte aligned
+    float* row_ss_out;         // folded RMS norm: per-row sums of squares out / in (tensor-core direct epilogues only)
+    const float* row_ss_in;
+    float rs_inv_dim, rs_eps;
 };
 
 inline EpiParams make_epi_params(const svc_gemm_desc& d) {
@@ -47,6 +50,10 @@ inline EpiParams make_epi_params(const svc_gemm_desc& d) {
     e.rope_cols = d.rope_cols;
     e.rope_pos0 = d.rope_pos0;
     e.rope_mod = 0;
+    e.row_ss_out = d.row_ss_out;
+    e.row_ss_in = d.row_ss_in;
+    e.rs_inv_dim = d.rs_inv_dim;
+    e.rs_eps = d.rs_eps;
     e.q_cols = d.q_cols;
     e.q_scale = d.q_scale;
     e.gate = d.gate;

@@ -119,12 +119,23 @@ __device__ __forceinline__ float fast_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#ifdef SVC_SIGMOID_EX2
+__device__ __forceinline__ float fast_sigmoid(float x) { return fast_rcp(1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_silu(float x) { return x * fast_sigmoid(x); }
+#else
+// one MUFU instead of two (ex2 + rcp): sigmoid(x) = 0.5 + 0.5 tanh(x / 2).  The SwiGLU / gate epilogues are bound by
+// the MUFU pipe (8 cycles per warp instruction, two epilogue warps per sub-partition); |error| <= 2^-12
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
+__device__ __forceinline__ float fast_silu(float x) {
+    const float h = 0.5f * x;
+    return fmaf(h, fast_tanh(h), h);
+}
+#endif
 
 struct EpiChunk {
     int co, c0;        // outputs per row in this chunk (32, or 16 after a pair activation), first column
@@ -205,10 +216,10 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const EpiParams& e, con
     }
     if (e.act == SVC_ACT_SILU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[j]);
     } else if (e.act == SVC_ACT_SWIGLU_PAIR) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = v[2 * j] * fast_sigmoid(v[2 * j]) * v[2 * j + 1];
+        for (int j = 0; j < 16; ++j) v[j] = fast_silu(v[2 * j]) * v[2 * j + 1];
     } else if (e.act == SVC_ACT_TANH_SIG_PAIR) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fast_tanh(v[2 * j]) * fast_sigmoid(v[2 * j + 1]);
@@ -386,10 +397,10 @@ __device__ __forceinline__ void epilogue_item_tma(const TcParams& p, float* stag
     }
     if (e.act == SVC_ACT_SILU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[j]);
     } else if (PAIR && e.act == SVC_ACT_SWIGLU_PAIR) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[2 * j] * fast_sigmoid(v[2 * j]) * v[2 * j + 1];
+        for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[2 * j]) * v[2 * j + 1];
     } else if (PAIR && e.act == SVC_ACT_TANH_SIG_PAIR) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[2 * j]) * fast_sigmoid(v[2 * j + 1]);
@@ -511,7 +522,9 @@ __device__ __forceinline__ void res_prefetch_rows(const EpiParams& e, int c0, in
 //   0 generic (every check at run time)      1 no vector operand; act = none or (pair) SwiGLU
 //   2 interleaved-pair RoPE, nothing else     3 bias only (+ row-layout residual in the two-output epilogue)
 //   4 per-batch bias + tanh * sigmoid pair (WaveNet in-layers)   5 residual only, two outputs (w2 / wo with an operand copy)
-constexpr int EK_GENERIC = 0, EK_PLAIN = 1, EK_ROPE = 2, EK_BIAS = 3, EK_ROWBIAS_TS = 4, EK_RES = 5;
+//   6 / 7 folded RMS norm: row scale (rs) + bias, then RoPE / SwiGLU pair
+constexpr int EK_GENERIC = 0, EK_PLAIN = 1, EK_ROPE = 2, EK_BIAS = 3, EK_ROWBIAS_TS = 4, EK_RES = 5, EK_RS_ROPE = 6,
+              EK_RS_SWIGLU = 7;
 
 // rbar / ridx: two-output epilogue with a TMA-loaded residual - the item's residual tile arrives in fp32 staging
 // buffer (ridx & 1) under mbarrier rbar[ridx & 1]; the finished fp32 tile is written over it and stored from there.
@@ -519,12 +532,13 @@ template <bool PAIR, int EK, bool DUAL>
 __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* stage, int lane, int b,
                                                      int t_base, int n0_acc, float (&v)[PAIR ? 64 : 32],
                                                      const float4 (&rr)[8], uint64_t* rbar = nullptr,
-                                                     uint32_t ridx = 0) {
+                                                     uint32_t ridx = 0, float rs = 1.0f) {
     const EpiParams& e = p.epi;
     constexpr int NA = PAIR ? 64 : 32;
     constexpr bool G = EK == EK_GENERIC;
     const int c0 = PAIR ? (n0_acc >> 1) : n0_acc;          // first output column
-    const bool has_bias = G ? e.bias != nullptr : EK == EK_BIAS;
+    constexpr bool RS = EK == EK_RS_ROPE || EK == EK_RS_SWIGLU;
+    const bool has_bias = G ? e.bias != nullptr : (EK == EK_BIAS || RS);
     const bool has_rowbias = G ? e.rowbias != nullptr : EK == EK_ROWBIAS_TS;
     const bool has_gate = G ? e.gate != nullptr : false;
     const bool has_res = G ? p.res_rows != 0 : EK == EK_RES ? true : (EK == EK_BIAS && DUAL && p.res_rows != 0);
@@ -532,9 +546,13 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     uint8_t* const fbuf = reinterpret_cast<uint8_t*>(stage) + ((DUAL && res_tma) ? (ridx & 1) * 4096 : 0);
     const bool has_alpha = G ? e.alpha != 1.0f : false;
     const int act = G ? e.act
-                      : EK == EK_ROPE ? SVC_ACT_ROPE
+                      : (EK == EK_ROPE || EK == EK_RS_ROPE) ? SVC_ACT_ROPE
                       : EK == EK_ROWBIAS_TS ? SVC_ACT_TANH_SIG_PAIR
-                      : (EK == EK_PLAIN && PAIR) ? SVC_ACT_SWIGLU_PAIR : SVC_ACT_NONE;
+                      : ((EK == EK_PLAIN && PAIR) || EK == EK_RS_SWIGLU) ? SVC_ACT_SWIGLU_PAIR : SVC_ACT_NONE;
+    if constexpr (RS) {     // folded RMS norm: this row's 1 / rms before the (folded) bias
+#pragma unroll
+        for (int j = 0; j < NA; ++j) v[j] *= rs;
+    }
     if (has_bias) {
 #pragma unroll
         for (int j = 0; j < NA; j += 4)
@@ -554,10 +572,10 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     }
     if (act == SVC_ACT_SILU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= fast_sigmoid(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[j]);
     } else if (PAIR && act == SVC_ACT_SWIGLU_PAIR) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[2 * j] * fast_sigmoid(v[2 * j]) * v[2 * j + 1];
+        for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[2 * j]) * v[2 * j + 1];
     } else if (PAIR && act == SVC_ACT_TANH_SIG_PAIR) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[2 * j]) * fast_sigmoid(v[2 * j + 1]);
@@ -653,6 +671,7 @@ __device__ __forceinline__ int epi_kind(const TcParams& p, bool pair, bool dual)
     }
     if (b && !rb && !pair && e.act == SVC_ACT_NONE && (dual || !rs)) return EK_BIAS;
     if (!b && !rb && rs && dual && !pair && e.act == SVC_ACT_NONE) return EK_RES;
+    if (e.row_ss_in != nullptr && b && !rb && !rs) return pair ? EK_RS_SWIGLU : EK_RS_ROPE;   // host-validated
     if (rb && !b && !rs && pair && e.act == SVC_ACT_TANH_SIG_PAIR) return EK_ROWBIAS_TS;
     return EK_GENERIC;
 }
@@ -847,7 +866,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         else g_cur = epi_chunk_geom(p.epi, cur.n0c);
         float4 rr_cur[8], rr_nxt[8];
         const bool want_prefetch = EK == EK_GENERIC && !direct && (!tma_mode || p.epi.act == SVC_ACT_ROPE);
-        const bool rope_direct = EK == EK_GENERIC ? (direct && p.epi.act == SVC_ACT_ROPE) : EK == EK_ROPE;
+        const bool rope_direct = EK == EK_GENERIC ? (direct && p.epi.act == SVC_ACT_ROPE) : (EK == EK_ROPE || EK == EK_RS_ROPE);
+        // folded RMS norm: this thread's row scale (consumer) / running sum of squares of its row (producer)
+        constexpr bool rs_in = EK == EK_RS_ROPE || EK == EK_RS_SWIGLU;
+        const bool ss_out = EPI == 5 && p.epi.row_ss_out != nullptr;
+        float rs_row = 1.0f, ss_acc = 0.f;
         if (cur.valid && want_prefetch && g_cur.vec && cur.t_base < p.T)
             epi_prefetch(p.epi, g_cur, lane, cur.b, cur.t_base, p.T, rr_cur);
         if (rope_direct && cur.valid && cur.n0c < p.epi.rope_cols)
@@ -873,6 +896,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         while (cur.valid) {
             if (tr_on) GTRACE(0, tr_i, 0);
             if (cur.step == 0) {
+                if constexpr (rs_in) {
+                    const int t = cur.t_base + lane;
+                    if (t < p.T) {
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(
+                            p.epi.row_ss_in + (static_cast<long long>(cur.b) * p.T + t) * SVC_SS_SLOTS));
+                        rs_row = rsqrtf(((q.x + q.y) + (q.z + q.w)) * p.epi.rs_inv_dim + p.epi.rs_eps);
+                    }
+                }
                 mbar_wait(&tmem_full_bar[group], (cur.it >> 1) & 1);
                 tc_fence_after();
             }
@@ -921,14 +952,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     float v[64];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]), v[32 + j] = __uint_as_float(r2[j]);
-                    if constexpr (direct) epilogue_item_direct<true, EK, EPI == 5>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                    if constexpr (direct) epilogue_item_direct<true, EK, EPI == 5>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur, nullptr, 0, rs_row);
                     else epilogue_item_tma<true>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
                 } else {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if constexpr (direct) epilogue_item_direct<false, EK, EPI == 5>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur, rbar, r_used);
+                    if constexpr (direct) epilogue_item_direct<false, EK, EPI == 5>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur, rbar, r_used, rs_row);
                     else epilogue_item_tma<false>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rr_cur);
+                    if constexpr (EPI == 5) {
+                        if (ss_out) {           // v holds the final fp32 values of this row's 32 columns
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) ss_acc = fmaf(v[j], v[j], ss_acc);
+                            if (cur.last) {
+                                const int t = cur.t_base + lane;
+                                if (t < p.T)
+                                    p.epi.row_ss_out[(static_cast<long long>(cur.b) * p.T + t) * SVC_SS_SLOTS + cur.n0 / BN] = ss_acc;
+                                ss_acc = 0.f;
+                            }
+                        }
+                    }
                 }
                 ++r_used;
             }
@@ -953,6 +996,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             if constexpr (EPI == 4) run_items(std::integral_constant<int, EK_ROWBIAS_TS>{});
         } else if (EPI == 5 && ek == EK_RES) {
             if constexpr (EPI == 5) run_items(std::integral_constant<int, EK_RES>{});
+        } else if (EPI == 3 && ek == EK_RS_ROPE) {
+            if constexpr (EPI == 3) run_items(std::integral_constant<int, EK_RS_ROPE>{});
+        } else if (EPI == 4 && ek == EK_RS_SWIGLU) {
+            if constexpr (EPI == 4) run_items(std::integral_constant<int, EK_RS_SWIGLU>{});
         } else {
             run_items(ek0{});
         }
@@ -1291,6 +1338,20 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
         }
     }
     if (BN < 64 && pair_act) p.store_mode = 0;
+    if (d.row_ss_in != nullptr) {
+        const bool ok = d.bias != nullptr && d.rowbias == nullptr && d.gate == nullptr && d.res == nullptr &&
+                        !d.accumulate && d.alpha == 1.0f && p.direct && p.store_mode == 1 &&
+                        (d.act == SVC_ACT_ROPE || d.act == SVC_ACT_SWIGLU_PAIR) &&
+                        reinterpret_cast<uintptr_t>(d.row_ss_in) % 16 == 0;
+        if (!ok) {
+            svc_set_error("svc_gemm: row_ss_in needs bias + RoPE / SwiGLU-pair -> out_op on the row-layout tensor-core epilogue");
+            return SVC_ERR_UNSUPPORTED;
+        }
+    }
+    if (d.row_ss_out != nullptr && !(p.dual && d.N % 32 == 0 && p.n_tiles <= SVC_SS_SLOTS)) {
+        svc_set_error("svc_gemm: row_ss_out needs the two-output tensor-core epilogue, N % 32 == 0 and <= 4 N tiles");
+        return SVC_ERR_UNSUPPORTED;
+    }
     if (flattened && rope_mod > 0 && !(p.direct && p.store_mode == 1)) {
         svc_set_error("svc_gemm: internal - flattened RoPE GEMM did not get the row-layout epilogue");
         return SVC_ERR_ARG;
@@ -1307,6 +1368,10 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
 }
 
 static int gemm_simt(const svc_gemm_desc& d, cudaStream_t stream) {
+    if (d.row_ss_in != nullptr || d.row_ss_out != nullptr) {
+        svc_set_error("svc_gemm: row_ss_in / row_ss_out exist on the tensor-core path only");
+        return SVC_ERR_UNSUPPORTED;
+    }
     SimtParams p;
     memset(&p, 0, sizeof(p));
     for (int s = 0; s < d.n_seg; ++s)

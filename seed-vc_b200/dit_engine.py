@@ -110,6 +110,8 @@ class DiTEngine:
 
         w = {}
         layers = []
+        # v1 RMS norms folded into the GEMMs around them (see fold_begin): needs the fp32 masters of wqkv / w13
+        self.fold = bool(getattr(ops, "fold_norms", False)) and sp.version == 1
         ada_w, ada_b = [], []          # stacked AdaLN projections, fp32
         ada_index = {}
 
@@ -130,6 +132,10 @@ class DiTEngine:
                                             sd[lp + "feed_forward.w3.weight"].float()), od),
                 "w2": dev(sd[lp + "feed_forward.w2.weight"], od),
             }
+            if self.fold:
+                lw["wqkv_f32"] = dev(sd[lp + "attention.wqkv.weight"])
+                lw["w13_f32"] = dev(_interleave_rows(sd[lp + "feed_forward.w1.weight"].float(),
+                                                     sd[lp + "feed_forward.w3.weight"].float()))
             if sp.version == 1:
                 lw["g_attn"] = dev(sd[lp + "attention_norm.norm.weight"])
                 lw["g_ffn"] = dev(sd[lp + "ffn_norm.norm.weight"])
@@ -373,6 +379,7 @@ class DiTEngine:
                 ops.gemm([(t1, 0, w["ada_w"])], n_ada, B=1, T=N, bias=w["ada_b"], out_f32=ada,
                          f32=True)
         st["ada"] = ada[0]                                 # (N, n_ada)
+        self.st_ada = ada[0]
         if sp.head == "wavenet":
             t2, _ = t_embed("t_embedder2")
             ng = w["wn_cond_w"].shape[0]
@@ -462,9 +469,59 @@ class DiTEngine:
             st["ln"] = torch.empty(R, T, Dw, dtype=sdt, device=dev)
             st["y"] = torch.empty(R, T, Dw, dtype=sdt, device=dev)
             st["wn_lens"] = st["x_lens"].repeat(nb).contiguous()
+        if self.fold:
+            self._fold_begin(st, N, R, Tq, dev)
         self.st = st
         st["c_state"] = self._c_state(st) if hasattr(ops, "dit_step") else None
         return st
+
+    # ------------------------------------------------------------------ folded RMS norms (v1)
+    def _copy_dtype(self, i):
+        """dtype of the operand copy of h that layer i's wqkv reads: the previous layer's w2 writes it; when that
+        layer is a U-ViT emit layer the copy IS the skip tensor (stream dtype)."""
+        sp = self.spec
+        emit_prev = sp.uvit and (i - 1) < sp.L // 2
+        return self.ops.stream_dtype if emit_prev else self.ops.op_dtype
+
+    def _fold_begin(self, st, N, R, Tq, dev):
+        """AdaptiveLayerNorm over RMSNorm feeding a Linear (diffusion_transformer.py:30-48, 173-191):
+            (h * r * g * w_s + b_s) W^T  =  r * (h (W * g * w_s)^T) + b_s W^T,   r = rsqrt(mean(h^2) + eps) per row,
+        so per Euler step s and layer the weight W'_s = W * (g * w_s) and the bias b_s W^T are prepared here (fp32
+        masters, one rounding), the GEMM that produces h also writes a 16-bit copy and the row sums of squares
+        (row_ss_out) and wqkv / w13 scale their accumulator rows (row_scale).  Removes both norm passes of a
+        layer; layer 0's attention norm (h assembled from several launches) and the final norm stay kernels."""
+        sp, ops, w = self.spec, self.ops, self.w
+        D, L = sp.D, sp.L
+        f32 = torch.float32
+        S = 1 if sp.time_as_token else N
+        st["fold_S"] = S
+        st["ss"] = torch.zeros(R * Tq, 4, dtype=f32, device=dev)          # SVC_SS_SLOTS
+        st["hn"] = torch.empty(R, Tq, D, dtype=ops.op_dtype, device=dev)   # copy of h for wqkv (non-skip layers)
+        st["hn2"] = torch.empty(R, Tq, D, dtype=ops.op_dtype, device=dev)  # copy of h for w13
+        fw = []
+        for i in range(L):
+            lw = w["layers"][i]
+            e = {}
+            for side, gname, wname, n_out in (("q", "g_attn", "wqkv_f32", 3 * D), ("f", "g_ffn", "w13_f32", 2 * sp.I)):
+                if side == "q" and i == 0:
+                    continue
+                mul = add = None
+                if not sp.time_as_token:
+                    a = self._ada_all(("attn" if side == "q" else "ffn") + str(i))     # (N, 2D): weight, bias
+                    mul, add = a[:, :D], a[:, D:]
+                dt = self._copy_dtype(i) if side == "q" else ops.op_dtype
+                Wf = torch.empty(S, n_out, D, dtype=dt, device=dev)
+                ops.scale_cols(lw[wname], lw[gname], mul, Wf)
+                rb = torch.zeros(1, S, n_out, dtype=f32, device=dev)
+                if add is not None:
+                    ops.gemm([(add.unsqueeze(0), 0, lw[wname])], n_out, B=1, T=S, out_f32=rb, f32=True)
+                e["w" + side], e["b" + side] = Wf, rb[0]
+            fw.append(e)
+        st["fold_w"] = fw
+
+    def _ada_all(self, name):
+        lo, n = self.w["ada_index"][name]
+        return self.st_ada[:, lo:lo + n]
 
     def launches_per_step(self):
         """Kernel launches of one estimator call (for the gpu_launches bookkeeping of the C path)."""
@@ -472,6 +529,8 @@ class DiTEngine:
         nb, L = st["nb"], sp.L
         n = nb + int(sp.time_as_token) + (nb if sp.style_as_token else 0)
         n += L * 7 + (L - L // 2 - 1 if sp.uvit else 0) + 1
+        if self.fold:
+            n -= 2 * L - 1
         n += nb if sp.long_skip else 0
         n += 2 if sp.head == "mlp" else (2 + sp.wn_layers + 2 * (sp.wn_layers - 1) + 1 + 3)
         return n
@@ -481,13 +540,61 @@ class DiTEngine:
         lo, n = self.w["ada_index"][name]
         return self.st["ada"][s, lo:lo + n]
 
+    def _layers_folded(self, s, rope, emit, recv):
+        """The transformer layers with the RMS norms folded into the GEMMs (see _fold_begin)."""
+        sp, ops, w, st = self.spec, self.ops, self.w, self.st
+        D, L, H = sp.D, sp.L, sp.H
+        R, Tq = st["nb"] * st["B"], st["Tq"]
+        h, xn, qkv, att, ff = st["h"], st["xn"], st["qkv"], st["att"], st["ff"]
+        ss, hn, hn2 = st["ss"], st["hn"], st["hn2"]
+        fs = 0 if st["fold_S"] == 1 else s
+        skips, skip_bufs = [], list(st["skips"])
+        a_in = None                     # operand copy of h for this layer's wqkv (None: layer 0, norm kernel)
+        for i in range(L):
+            lw, fw = w["layers"][i], st["fold_w"][i]
+            if i in recv:
+                skip = skips.pop()
+                ops.gemm([(st["h_op"], 0, lw["skip_w"][:, :D]), (skip, 0, lw["skip_w"][:, D:])], D,
+                         B=R, T=Tq, bias=lw["skip_b"], out_f32=h, out_op=hn, row_ss_out=ss)
+                a_in = hn
+            if a_in is None:
+                if sp.time_as_token:
+                    ops.norm_mod(h, xn, gamma=lw["g_attn"])
+                else:
+                    a = self._ada(s, f"attn{i}")
+                    ops.norm_mod(h, xn, gamma=lw["g_attn"], mul=a[:D], add=a[D:])
+                ops.gemm([(xn, 0, lw["wqkv"])], 3 * D, B=R, T=Tq, act=ACT_ROPE, rope=rope, out_op=qkv)
+            else:
+                ops.gemm([(a_in, 0, fw["wq"][fs])], 3 * D, B=R, T=Tq, bias=fw["bq"][fs], act=ACT_ROPE, rope=rope,
+                         out_op=qkv, row_scale=(ss, D, 1e-5))
+            ops.attention(qkv, att, H, st["kv_len"])
+            ops.gemm([(att, 0, lw["wo"])], D, B=R, T=Tq, res=h, out_f32=h, out_op=hn2, row_ss_out=ss)
+            ops.gemm([(hn2, 0, fw["wf"][fs])], 2 * sp.I, B=R, T=Tq, bias=fw["bf"][fs], act=ACT_SWIGLU_PAIR,
+                     out_op=ff, row_scale=(ss, D, 1e-5))
+            # w2 also writes the operand copy its consumer reads: the skip tensor (emit layers: next wqkv reads
+            # the skip buffer itself), h_op (skip_in_linear of a receive layer comes next), or hn
+            nxt_recv = (i + 1) in recv
+            if i in emit:
+                copy = skip_bufs.pop(0)
+                skips.append(copy)
+            elif nxt_recv:
+                copy = st["h_op"]
+            else:
+                copy = hn if i + 1 < L else None
+            direct = copy is not None and not nxt_recv          # next layer's wqkv consumes (copy, ss) directly
+            ops.gemm([(ff, 0, lw["w2"])], D, B=R, T=Tq, res=h, out_f32=h, out_op=copy,
+                     row_ss_out=ss if direct else None)
+            assert not (i in emit and nxt_recv)
+            a_in = copy if direct else None
+            assert a_in is None or a_in.dtype == self._copy_dtype(i + 1)
+
     def step(self, s, x_op):
         """Velocity of every branch at step ``s``: (nb*B, T, C) fp32.  x_op: (B, T, C).
 
         On the CUDA library this is ONE call of the graph-level C entry point ``svc_dit_step`` (csrc/graph.cu),
         which issues exactly the launch sequence written out below; the Python sequence runs when per-launch
         profiling is on (bench.py's kernel breakdown) and on the emulated ops of the CPU host-logic tests."""
-        if self.st.get("c_state") is not None and self.ops.profile is None:
+        if self.st.get("c_state") is not None and self.ops.profile is None and not self.fold:
             assert x_op.is_contiguous() and x_op.dtype == self.ops.stream_dtype
             self.ops.dit_step(self._c_weights(), self.st["c_state"], s, x_op, self.launches_per_step())
             return self.st["v"]
@@ -520,7 +627,9 @@ class DiTEngine:
         skips = []
         skip_bufs = list(st["skips"])
         pending_raw = None        # skip tensor of the previous (emit) layer: written by this layer's first norm
-        for i in range(L):
+        if self.fold:
+            self._layers_folded(s, rope, emit, recv)
+        for i in range(L if not self.fold else 0):
             lw = w["layers"][i]
             if i in recv:
                 skip = skips.pop()

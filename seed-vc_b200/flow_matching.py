@@ -202,10 +202,10 @@ class DiT(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("seedvc_b200.DiT runs on CUDA only: call .to('cuda') first "
                                "(there is no CPU fallback)")
-        key = (str(dev), self.mode, tuple(p._version for p in self.parameters()),
+        key = (str(dev), self.mode, getattr(self, "fold_norms", False), tuple(p._version for p in self.parameters()),
                tuple(p.data_ptr() for p in self.parameters()))
         if self._engine is None or key != self._engine_key:
-            eng = DiTEngine(self.spec, Ops(self.mode))
+            eng = DiTEngine(self.spec, Ops(self.mode, fold_norms=getattr(self, "fold_norms", False)))
             eng.load_weights(self.state_dict(), dev)
             if self.max_seq_length > 0:
                 eng.setup_rope(self.max_seq_length, dev)

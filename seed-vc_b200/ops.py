@@ -27,7 +27,7 @@ def _ptr(t):
 
 
 class Ops:
-    def __init__(self, mode: str = "bf16", force_simt: bool = False):
+    def __init__(self, mode: str = "bf16", force_simt: bool = False, fold_norms: bool = False):
         if mode not in MODES:
             raise ValueError("mode must be 'fp16', 'bf16' or 'fp32'")
         self.lib = _lib.load_library()
@@ -41,6 +41,11 @@ class Ops:
         self.stream_dtype = torch.float16 if mode == "bf16" else self.op_dtype
         self.backend = BACKEND_SIMT if force_simt else BACKEND_AUTO
         self.precise = 1 if mode == "fp32" else 0
+        # RMS norms folded into the GEMMs around them (svc_gemm_desc.row_ss_*; tensor-core epilogues only).  OFF by
+        # default: measured on config 2 it saves the two norm passes of a layer (2 x 98 us) but the K = 512 GEMMs
+        # are epilogue-bound, and the row scale + bias in the wqkv / w13 epilogues (+96 / +121 us) and the second
+        # output of wo / w2 (+38 / +59 us) cost more than that (44.2 against 41.7 ms per Euler step).
+        self.fold_norms = bool(fold_norms) and mode != "fp32" and not force_simt
         self.launches = 0
         self._rope_t = {}        # rope table data_ptr -> (table, pair-major copy)
         self.use_rope_t = True   # False: pass only the position-major table (exercises the fallback epilogue)
@@ -104,11 +109,13 @@ class Ops:
     # ------------------------------------------------------------------ GEMM
     def gemm(self, segs, N, *, B, T, bias=None, rowbias=None, act=ACT_NONE, rope=None, gate=None,
              res=None, alpha=1.0, accumulate=False, out_f32=None, out_op=None, f32=False,
-             algo_flops=None):
+             algo_flops=None, row_ss_out=None, row_scale=None):
         """out[b,t,:] = epilogue(sum_s A_s[b, t+shift_s, :] @ W_s.T); see svc_gemm.
 
         segs: [(A (B, rows, K), shift, W (N, K))]; rope: (table, rope_cols, pos0, q_cols, q_scale).
         ``f32=True`` forces fp32 operands whatever the mode (small conditioning GEMMs).
+        Folded RMS norm (svc_gemm_desc.row_ss_*): ``row_ss_out`` (B*T, 4) fp32 receives the row sums of squares of
+        the fp32 output; ``row_scale=(ss, dim, eps)`` scales accumulator row r by rsqrt(sum(ss[r]) / dim + eps).
         """
         d = GemmDesc()
         dt = segs[0][0].dtype              # operand type of this call: fp32, or one of the 16-bit formats
@@ -166,6 +173,16 @@ class Ops:
                 d.out_op_dtype_p1 = 1 + self._code(out_op.dtype)
             d.out_op = out_op.data_ptr()
             d.oo_bstride, d.oo_rstride = out_op.stride(0), out_op.stride(1)
+        if row_ss_out is not None:
+            self._chk(row_ss_out)
+            assert row_ss_out.dtype == torch.float32 and row_ss_out.is_contiguous()
+            assert row_ss_out.shape == (B * T, _lib.SS_SLOTS)
+            d.row_ss_out = row_ss_out.data_ptr()
+        if row_scale is not None:
+            ss, dim, eps = row_scale
+            self._chk(ss)
+            assert ss.dtype == torch.float32 and ss.is_contiguous() and ss.shape == (B * T, _lib.SS_SLOTS)
+            d.row_ss_in, d.rs_inv_dim, d.rs_eps = ss.data_ptr(), 1.0 / float(dim), float(eps)
         ktot = sum(W.shape[1] for _, _, W in segs)
         cat = "gemm_f32" if dt == torch.float32 else ("gemm_tc" if self.backend == BACKEND_AUTO
                                                                else "gemm_simt")
@@ -309,6 +326,20 @@ class Ops:
         self._t0("misc")
         check(self.lib.svc_cast(inp.data_ptr(), out.data_ptr(), inp.numel(), self._code(out.dtype),
                                 self._stream()), "svc_cast")
+        self._t1()
+
+    def scale_cols(self, W, g, mul, out):
+        """out[s] = W * g[None, :] * mul[s][None, :]  (folded RMS norm: weight side).  W (N, K) fp32, g (K,) or
+        None, mul (S, K) fp32 view or None, out (S, N, K) in any operand dtype."""
+        self._chk(W, g, mul, out)
+        S, N, K = out.shape
+        assert W.dtype == torch.float32 and W.shape == (N, K) and W.stride(1) == 1 and out.is_contiguous()
+        assert mul is None or (mul.shape == (S, K) and mul.stride(1) == 1 and mul.dtype == torch.float32)
+        assert mul is not None or S == 1
+        self._t0("misc")
+        check(self.lib.svc_scale_cols(W.data_ptr(), W.stride(0), _ptr(g), _ptr(mul),
+                                      mul.stride(0) if mul is not None else 0, out.data_ptr(),
+                                      self._code(out.dtype), S, N, K, self._stream()), "svc_scale_cols")
         self._t1()
 
     def reflect_halo(self, buf, T, pad, lens=None):

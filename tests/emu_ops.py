@@ -15,8 +15,9 @@ ACT_NONE, ACT_SILU, ACT_SWIGLU_PAIR, ACT_TANH_SIG_PAIR, ACT_ROPE = 0, 1, 2, 3, 4
 
 
 class EmuOps:
-    def __init__(self, mode="fp32"):
+    def __init__(self, mode="fp32", fold_norms=False):
         self.mode = "fp32"
+        self.fold_norms = fold_norms      # exercise the engine's folded-norm orchestration on the emulated ops
         self.op_dtype = torch.float32
         self.stream_dtype = torch.float32
         self.launches = 0
@@ -29,7 +30,7 @@ class EmuOps:
 
     def gemm(self, segs, N, *, B, T, bias=None, rowbias=None, act=ACT_NONE, rope=None, gate=None,
              res=None, alpha=1.0, accumulate=False, out_f32=None, out_op=None, f32=False,
-             algo_flops=None):
+             algo_flops=None, row_ss_out=None, row_scale=None):
         self.launches += 1
         dev = segs[0][0].device
         acc = torch.zeros(B, T, N, device=dev)
@@ -42,6 +43,9 @@ class EmuOps:
             a[:, ok] = A[:, idx[ok]].float()
             acc += a @ W.float().t()
         v = acc
+        if row_scale is not None:      # folded RMS norm: accumulator rows scaled by 1 / rms of the producer's rows
+            ss, dim, eps = row_scale
+            v = v * torch.rsqrt(ss.sum(-1).view(B, T, 1) / dim + eps)
         if bias is not None:
             v = v + bias.view(1, 1, N)
         if rowbias is not None:
@@ -72,6 +76,9 @@ class EmuOps:
             out_f32.copy_(v)
         if out_op is not None:
             out_op.copy_(v)
+        if row_ss_out is not None:     # all of the row's sum of squares in slot 0 (consumers add the slots)
+            row_ss_out.zero_()
+            row_ss_out[:, 0] = (v * v).sum(-1).reshape(B * T)
 
     def attention(self, qkv, out, H, kv_len):
         self.launches += 1
@@ -154,6 +161,15 @@ class EmuOps:
     def cast(self, inp, out):
         self.launches += 1
         out.copy_(inp.view(out.shape))
+
+    def scale_cols(self, W, g, mul, out):
+        self.launches += 1
+        w = W.unsqueeze(0)
+        if g is not None:
+            w = w * g.view(1, 1, -1)
+        if mul is not None:
+            w = w * mul.unsqueeze(1)
+        out.copy_(w.expand(out.shape))
 
     def reflect_halo(self, buf, T, pad, lens=None):
         self.launches += 1

@@ -66,6 +66,32 @@ def test_v1_golden(name, mode):
     assert e_v < TOL[mode] and e_o < TOL[mode]
 
 
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", ["v1_small_full", "v1_tiny_full", "v1_base_scaled_cfg"])
+def test_v1_golden_folded_norms(name, mode):
+    """The optional folded-RMS-norm path (Ops(fold_norms=True): svc_gemm row_ss_out / row_ss_in, DiTEngine._fold_begin)
+    against the same reference goldens; off by default because it measures slower (see Ops.fold_norms)."""
+    g = load_golden(name)
+    m = g["meta"]
+    cfm, args = v1_model(m["model"], m["scaled"], mode)
+    est = cfm.estimator
+    est.fold_norms = True
+    try:
+        assert est.engine().fold
+        T, Tp = m["T"], m["Tp"]
+        mu, prompt, style, z = [t.to(DEV) for t in
+                                synth.synth_batch(1, T, Tp, args.DiT.in_channels, args.DiT.content_dim)]
+        t_span = torch.linspace(0, 1, m["n_steps"] + 1, device=DEV)
+        xl = torch.tensor([T], device=DEV)
+        out = cfm.solve_euler(z.clone(), xl, prompt, mu, style, None, t_span, m["cfg"])
+        e_o = rel_l2(out.cpu(), g["out"])
+        print(f"{name} [{mode}, folded norms] end-to-end rel-L2 {e_o:.2e}")
+        assert e_o < TOL[mode]
+    finally:
+        est.fold_norms = False
+    assert not est.engine().fold
+
+
 @pytest.mark.parametrize("mode", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("name", V2)
 def test_v2_golden(name, mode):

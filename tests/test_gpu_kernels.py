@@ -171,6 +171,53 @@ def test_gemm_segments(mode, simt):
             run_gemm_case(mode, simt, 1, 64, 32, [32] * 5)
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+@pytest.mark.parametrize("D,T", [(512, 333), (384, 150), (768, 200)])
+def test_gemm_folded_rms_norm(mode, D, T):
+    """svc_gemm_desc.row_ss_out / row_ss_in: the producer (residual + two outputs) reports the row sums of squares
+    of its fp32 output, the consumers (RoPE -> operand, SwiGLU pair -> operand) scale their accumulator rows by
+    1 / rms before the bias.  Checked against the unfused sequence norm -> GEMM in fp32 (AdaptiveLayerNorm over
+    RMSNorm, diffusion_transformer.py:30-48, with the per-column factors folded into the weight by the caller)."""
+    ops, emu = ops_for(mode), EmuOps()
+    od = ops.op_dtype
+    B, K = 3, 256
+    A = rnd(B, T, K, dtype=od)
+    Wp = rnd(D, K, seed=3, scale=1 / math.sqrt(K), dtype=od)
+    h0 = rnd(B, T, D, seed=4)
+    for inplace_bias in (None, rnd(D, seed=9)):
+        h, h_ref = h0.clone(), h0.clone()
+        h16 = torch.zeros(B, T, D, dtype=od, device=DEV)
+        ss = torch.zeros(B * T, 4, device=DEV)
+        ops.gemm([(A, 0, Wp)], D, B=B, T=T, bias=inplace_bias, res=h, out_f32=h, out_op=h16, row_ss_out=ss)
+        emu.gemm([(A, 0, Wp)], D, B=B, T=T, bias=inplace_bias, res=h_ref, out_f32=h_ref)
+        assert rel_l2(h, h_ref) < 3e-3
+        want_ss = (h.double() ** 2).sum(-1).reshape(B * T)
+        assert torch.allclose(ss.double().sum(-1), want_ss, rtol=2e-6)
+        assert torch.equal(h16, h.to(od))
+        # consumers: x_norm = h * rsqrt(mean(h^2) + eps) * g + a, then Linear W  ==  rs * (h16 (W * g)^T) + a W^T
+        g, a = torch.exp(0.2 * rnd(D, seed=5)), 0.3 * rnd(D, seed=6)
+        xn = h16.float() * torch.rsqrt((h * h).mean(-1, keepdim=True) + 1e-5) * g + a
+        from seedvc_b200.dit_engine import rope_table
+        tab = rope_table(T + 8).to(DEV)
+        for N, act, rope in ((3 * D, _lib.ACT_ROPE, (tab, 2 * D, 0, D, 0.125)), (2 * 640, _lib.ACT_SWIGLU_PAIR, None)):
+            W = rnd(N, D, seed=7, scale=1 / math.sqrt(D))
+            Wf = (W * g.view(1, D)).to(od)
+            bias = (W @ a).contiguous()
+            n_out = N // 2 if act == _lib.ACT_SWIGLU_PAIR else N
+            out = torch.zeros(B, T, n_out, dtype=od, device=DEV)
+            ref = torch.zeros(B, T, n_out, device=DEV)
+            ops.gemm([(h16, 0, Wf)], N, B=B, T=T, bias=bias, act=act, rope=rope, out_op=out,
+                     row_scale=(ss, D, 1e-5))
+            emu.gemm([(xn, 0, W)], N, B=B, T=T, act=act, rope=rope, out_f32=ref)
+            e = rel_l2(out.float(), ref)
+            assert e < (6e-3 if mode == "bf16" else 1.5e-3), f"{mode} D={D} act={act}: rel-L2 {e}"
+    if mode == "bf16":      # refused where the epilogue cannot do it, never silently ignored
+        with pytest.raises(_lib.SvcError):
+            ops.gemm([(A, 0, Wp)], D, B=B, T=T, out_f32=h, row_ss_out=ss)
+        with pytest.raises(_lib.SvcError):
+            ops.gemm([(h16, 0, Wp.new_zeros(D, D))], D, B=B, T=T, out_op=h16.clone(), row_scale=(ss, D, 1e-5))
+
+
 def test_gemm_conv_taps_share_weight_buffer():
     """Taps taken as slices of one (k, N, K) tensor (one TMA map, row offsets)."""
     ops, emu = ops_for("bf16"), EmuOps()

@@ -19,30 +19,33 @@ V2 = ["v2_small_3branch", "v2_small_spk_only", "v2_small_txt_only", "v2_small_no
       "v2_small_random_voice"]
 
 
-def emu_engine(estimator):
-    eng = DiTEngine(estimator.spec, EmuOps())
+def emu_engine(estimator, fold=False):
+    eng = DiTEngine(estimator.spec, EmuOps(fold_norms=fold))
     eng.load_weights(estimator.state_dict(), "cpu")
     estimator.engine = lambda: eng
     return eng
 
 
-def v1_case(name):
+def v1_case(name, fold=False):
     g = load_golden(name)
     m = g["meta"]
     args = configs.v1_model_params(m["model"])
     if m["scaled"]:
         args = configs.scaled_down(args)
     cfm = CFM(args)
-    emu_engine(cfm.estimator)
+    emu_engine(cfm.estimator, fold)
     cfm.estimator.setup_caches(1, 8192)
     mu, prompt, style, z = synth.synth_batch(1, m["T"], m["Tp"], args.DiT.in_channels,
                                              args.DiT.content_dim)
     return g, m, cfm, (mu, prompt, style, z)
 
 
+@pytest.mark.parametrize("fold", [False, True], ids=["norm_kernels", "folded_norms"])
 @pytest.mark.parametrize("name", V1)
-def test_v1_host_logic(name):
-    g, m, cfm, (mu, prompt, style, z) = v1_case(name)
+def test_v1_host_logic(name, fold):
+    """fold: the engine's folded-RMS-norm orchestration (DiTEngine._fold_begin / _layers_folded) on the emulated ops."""
+    g, m, cfm, (mu, prompt, style, z) = v1_case(name, fold)
+    assert cfm.estimator.engine().fold == fold
     T, Tp = m["T"], m["Tp"]
     t_span = torch.linspace(0, 1, m["n_steps"] + 1)
     x0 = z.clone()
@@ -192,8 +195,9 @@ def test_hift_oracle_matches_reference(manifest):
         assert rel_l2(orc.hift_f0_predictor(sd, mel), z[name + "_f0pred"]) < 2e-5
 
 
+@pytest.mark.parametrize("fold", [False, True], ids=["norm_kernels", "folded_norms"])
 @pytest.mark.parametrize("model,cfg", [("whisper_small", 0.7), ("xlsr_tiny", 0.7), ("whisper_base", 0.0), ("v2", (0.7, 0.7))])
-def test_launches_per_step_bookkeeping(model, cfg):
+def test_launches_per_step_bookkeeping(model, cfg, fold):
     """DiTEngine.launches_per_step (what the one-call C path adds to the launch counter) == the number of ops the
     written-out Python sequence issues for one estimator call."""
     T, Tp = 40, 10
@@ -206,7 +210,7 @@ def test_launches_per_step_bookkeeping(model, cfg):
         args = configs.scaled_down(configs.v1_model_params(model))
         cfm = CFM(args)
         C, cd = args.DiT.in_channels, args.DiT.content_dim
-    eng = emu_engine(cfm.estimator)
+    eng = emu_engine(cfm.estimator, fold)
     if model != "v2":
         cfm.estimator.setup_caches(1, 8192)
     counts = []
