@@ -556,6 +556,11 @@ def run_ours(a):
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": wl["scaling"],
         "vs_baseline": None, "dtype": a.mode, "data": "synthetic",
+        "dtype_detail": {"bf16": "bf16 operands on tcgen05 for the transformer-branch GEMMs and attention; IEEE half for "
+                                 "operands that carry a residual stream and for the whole vocoder; fp32 accumulation, "
+                                 "residual streams and norms",
+                         "fp16": "IEEE half operands on tcgen05; fp32 accumulation, residual streams and norms",
+                         "fp32": "fp32 FFMA kernels"}[a.mode],
         "config": describe(a.workload, wl, world),
         "batch_this_rank": B, "cuda_graph": graphed is not None,
         "ms_per_euler_step": round(euler_ms, 3) if euler_ms else None,

@@ -201,7 +201,10 @@ class BigVGAN(nn.Module):
         key = (str(dev), self.mode, tuple(p._version for p in self.parameters()),
                tuple(p.data_ptr() for p in self.parameters()))
         if self._w is None or key != self._w_key:
-            self._w, self._w_key = self._build_weights(Ops(self.mode)), key
+            # every GEMM operand of the vocoder is an un-normalised stream value (there is no norm layer in BigVGAN),
+            # so "bf16" mode runs it on IEEE-half operands like the other stream-carrying operands of that mode
+            # (Ops.stream_dtype): waveform rel-L2 1.2e-3 instead of 9.7e-3 of a 1e-2 budget for +1.6 % vocoder time
+            self._w, self._w_key = self._build_weights(Ops("fp16" if self.mode == "bf16" else self.mode)), key
         return self._w
 
     def _build_weights(self, ops):

@@ -686,15 +686,23 @@ template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
     using S = TcSmem<BN, STAGES, EPI == 5 ? kDualWarpBytes : 4096>;
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
-    constexpr int kTmemCols = 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;   // power of two
+    // accumulator buffers in TMEM: four when they fit (tiles up to 128 columns), else two.  With two, a buffer is busy
+    // from the first MMA of a tile to the last tcgen05.ld of its epilogue, so MMA and epilogue of the SAME group take
+    // turns; with four the MMA warp runs up to two tiles ahead and both epilogue groups always find a finished tile.
+#ifdef SVC_TMEM_NB2
+    constexpr int NB = 2;
+#else
+    constexpr int NB = 4 * ACC_COLS <= 512 ? 4 : 2;
+#endif
+    constexpr int kTmemCols = NB * ACC_COLS <= 64 ? 64 : NB * ACC_COLS <= 128 ? 128 : NB * ACC_COLS <= 256 ? 256 : 512;   // power of two
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
-    uint64_t* res_bar = tmem_empty_bar + 2;           // [kEpiWarps][2]: TMA-loaded residual items (EPI 5)
+    uint64_t* tmem_full_bar = empty_bar + STAGES;     // [4] (NB used)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 4;     // [4]
+    uint64_t* res_bar = tmem_empty_bar + 4;           // [kEpiWarps][2]: TMA-loaded residual items (EPI 5)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
 
     const int warp = threadIdx.x >> 5;
@@ -711,7 +719,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 4; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
             mbar_init(&tmem_empty_bar[a], kEpiWarps / 2);
         }
@@ -769,9 +777,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 int n_umma = p.epi.N - n0;
                 n_umma = n_umma > BN ? BN : ((n_umma + 15) & ~15);
                 const uint32_t idesc = umma_idesc_bf16(BM, n_umma, 0, 0, p.ab_f16 ? 0u : 1u);
-                const int acc = it & 1;
+                const int acc = it % NB;
                 GTRACE(1, it, 0);
-                mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);   // epilogue drained this buffer
+                mbar_wait(&tmem_empty_bar[acc], ((it / NB) & 1) ^ 1);   // epilogue drained this buffer
                 GTRACE(1, it, 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
@@ -806,7 +814,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         const int group = ew >> 2;
         const int lg = warp & 3;             // TMEM lane group this warp may access
         float* stage_buf = reinterpret_cast<float*>(smem + S::EPI_OFFSET + ew * S::EPI_WARP_BYTES);
-        const uint32_t taddr = tmem_base + group * ACC_COLS + (static_cast<uint32_t>(lg * 32) << 16);
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);   // + buffer (tile index % NB) * ACC_COLS
         constexpr bool tma_mode = EPI != 0;
         constexpr bool pair = EPI == 2 || EPI == 4;
         constexpr bool direct = EPI >= 3;          // 3 direct, 4 direct pair, 5 direct with two outputs
@@ -904,10 +912,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                         rs_row = rsqrtf(((q.x + q.y) + (q.z + q.w)) * p.epi.rs_inv_dim + p.epi.rs_eps);
                     }
                 }
-                mbar_wait(&tmem_full_bar[group], (cur.it >> 1) & 1);
+                mbar_wait(&tmem_full_bar[cur.it % NB], (cur.it / NB) & 1);
                 tc_fence_after();
             }
             uint32_t r[32], r2[pair ? 32 : 1];
+            const uint32_t taddr = taddr0 + (cur.it % NB) * ACC_COLS;
             tmem_ld_32x32(taddr + cur.ch * acc_per_item, r);
             if constexpr (pair) tmem_ld_32x32(taddr + cur.ch * 64 + 32, r2);
             const Item nxt = next_item(cur);
@@ -939,7 +948,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             if (cur.last) {                     // this warp has read its whole slice of the buffer
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[group]);
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[cur.it % NB]);
             }
             if (cur.t_base < p.T && !(SVC_DBG_BITS(p) & 1)) {
                 if constexpr (EPI == 0) {
@@ -1229,6 +1238,13 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
     else if (d.N <= 128) BN = 128;
     else if ((d.N == 192 || d.N == 384) && bn192) BN = 192;   // exact tiles: no half-empty second tile / W box
     else BN = 256;
+#ifdef SVC_PREFER_BN128
+    if (BN == 256) {
+        int ktot = 0;
+        for (int s = 0; s < d.n_seg; ++s) ktot += d.K[s];
+        if (ktot <= SVC_PREFER_BN128) BN = 128;
+    }
+#endif
     // ---- A maps: one per distinct view ---------------------------------------------------
     struct AKey { const void* ptr; long long bs, rs; int rows, K; };
     AKey akeys[kMaxMaps];
