@@ -24,7 +24,7 @@ $CMD > gpurun_out/ncu_plain3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:attention_tc_kernel -s 10 -c 2 -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_attn.log 2>&1
 echo "attention capture exit $?"; export_rep prof_attn
 $CMD > gpurun_out/ncu_plain4.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:snake_aa -s 30 -c 1 -o gpurun_out/prof_snake $CMD > gpurun_out/ncu_snake.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:snake_mma -s 30 -c 1 -o gpurun_out/prof_snake $CMD > gpurun_out/ncu_snake.log 2>&1
 echo "snake capture exit $?"; export_rep prof_snake
 # DRAM traffic of every gemm_tc_kernel launch of ONE config-2 conversion pass (bench default workload):
 # feeds roofline.traffic (profiles/<round>_gemm_traffic.json)
