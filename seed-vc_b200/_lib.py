@@ -40,7 +40,7 @@ class GemmDesc(C.Structure):
     ]
 
 
-SS_SLOTS = 4     # SVC_SS_SLOTS
+SS_SLOTS = 8     # SVC_SS_SLOTS
 
 
 MAX_LAYERS, MAX_WN_LAYERS, MAX_BRANCH = 32, 16, 3

@@ -495,7 +495,7 @@ class DiTEngine:
         f32 = torch.float32
         S = 1 if sp.time_as_token else N
         st["fold_S"] = S
-        st["ss"] = torch.zeros(R * Tq, 4, dtype=f32, device=dev)          # SVC_SS_SLOTS
+        st["ss"] = torch.zeros(R * Tq, 8, dtype=f32, device=dev)          # SVC_SS_SLOTS
         st["hn"] = torch.empty(R, Tq, D, dtype=ops.op_dtype, device=dev)   # copy of h for wqkv (non-skip layers)
         st["hn2"] = torch.empty(R, Tq, D, dtype=ops.op_dtype, device=dev)  # copy of h for w13
         fw = []

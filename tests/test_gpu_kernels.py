@@ -187,7 +187,7 @@ def test_gemm_folded_rms_norm(mode, D, T):
     for inplace_bias in (None, rnd(D, seed=9)):
         h, h_ref = h0.clone(), h0.clone()
         h16 = torch.zeros(B, T, D, dtype=od, device=DEV)
-        ss = torch.zeros(B * T, 4, device=DEV)
+        ss = torch.zeros(B * T, 8, device=DEV)
         ops.gemm([(A, 0, Wp)], D, B=B, T=T, bias=inplace_bias, res=h, out_f32=h, out_op=h16, row_ss_out=ss)
         emu.gemm([(A, 0, Wp)], D, B=B, T=T, bias=inplace_bias, res=h_ref, out_f32=h_ref)
         assert rel_l2(h, h_ref) < 3e-3
