@@ -42,6 +42,10 @@ struct alignas(64) TcParams {
     int n_seg, total_kb;
     int B, T, tiles_per_batch, n_tiles;
     int ab_f16;                // operands are IEEE half (else bf16)
+    // CTA pairs (cluster of 2 along M): both CTAs work on the same N tile of two adjacent M tiles, each TMA-loads
+    // HALF of the weight tile and multicasts it to the pair - the weight tile crosses L2 -> SM once per pair.
+    int mc, pair_tiles;
+    CUtensorMap wmap_h[kMaxMaps];   // weight maps with a box of BN / 2 rows
 #ifdef SVC_TRACE
     int dbg;   // trace builds only (SVC_DBG env): 1 = skip epilogue body, 2 = skip MMA issue (timing experiments)
 #endif
@@ -708,6 +712,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.B * p.tiles_per_batch * p.n_tiles;
+    const bool mc = p.mc != 0;
+    const int crank = mc ? static_cast<int>(blockIdx.x & 1) : 0;        // rank in the CTA pair (1-D grid, cluster 2)
+    // tile `it` of this CTA -> (m_tile, n_tile); pairs walk (m pair, n) with n fastest, rank = which M tile
+    auto tile_of = [&](int it, int& m_tile, int& n_tile) {
+        if (mc) {
+            const int pt = static_cast<int>(blockIdx.x >> 1) + it * static_cast<int>(gridDim.x >> 1);
+            if (pt >= p.pair_tiles) return false;
+            n_tile = pt % p.n_tiles;
+            m_tile = 2 * (pt / p.n_tiles) + crank;       // may lie one past the last M tile: computed on zeros, not stored
+            return true;
+        }
+        const int tile = blockIdx.x + it * gridDim.x;
+        if (tile >= total_tiles) return false;
+        n_tile = tile % p.n_tiles;
+        m_tile = tile / p.n_tiles;
+        return true;
+    };
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < kMaxMaps; ++i) {
@@ -717,7 +738,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         if (p.store_mode != 0) tma_prefetch_desc(&p.omap);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], mc ? 2 : 1);     // pair: the MMA warps of both CTAs release a stage
         }
         for (int a = 0; a < 4; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
@@ -733,6 +754,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (mc) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -741,9 +763,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.n_tiles;
-                const int m_tile = tile / p.n_tiles;
+            int m_tile, n_tile;
+            for (int it = 0; tile_of(it, m_tile, n_tile); ++it) {
                 const int b = m_tile / p.tiles_per_batch;
                 const int t0 = (m_tile % p.tiles_per_batch) * BM;
                 const int n0 = n_tile * BN;
@@ -755,8 +776,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                         uint8_t* sa = smem + stage * S::STAGE_BYTES;
                         tma_load_3d(sa, &p.amap[sg.a_map], &full_bar[stage], kb * BK, t0 + sg.shift, b);
                         // weight maps are rank 3 too (K, rows, 1): instruction rank == map rank
-                        tma_load_3d(sa + S::A_BYTES, &p.wmap[sg.w_map], &full_bar[stage], kb * BK,
-                                    sg.w_row0 + n0, 0);
+                        if (mc)     // this CTA's half of the weight tile, to both CTAs of the pair
+                            tma_load_3d_mc(sa + S::A_BYTES + crank * (S::B_BYTES / 2), &p.wmap_h[sg.w_map], &full_bar[stage],
+                                           kb * BK, sg.w_row0 + n0 + crank * (BN / 2), 0, 3);
+                        else
+                            tma_load_3d(sa + S::A_BYTES, &p.wmap[sg.w_map], &full_bar[stage], kb * BK,
+                                        sg.w_row0 + n0, 0);
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -772,8 +797,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             uint32_t phase = 0;
             int it = 0;
             const uint32_t a_lo0 = desc_lo(smem_u32(smem));
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int n0 = (tile % p.n_tiles) * BN;
+            int m_tile, n_tile;
+            for (; tile_of(it, m_tile, n_tile); ++it) {
+                const int n0 = n_tile * BN;
                 int n_umma = p.epi.N - n0;
                 n_umma = n_umma > BN ? BN : ((n_umma + 15) & ~15);
                 const uint32_t idesc = umma_idesc_bf16(BM, n_umma, 0, 0, p.ab_f16 ? 0u : 1u);
@@ -794,7 +820,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                             tc_mma_f16_lh(d_tmem, alo + k * 2, kDescHiSw128, blo + k * 2, kDescHiSw128,
                                           idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (mc) tc_commit_mc(&empty_bar[stage], 3);     // ... in both CTAs: the peer multicasts into this slot
+                    else tc_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -834,14 +861,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             Item x;
             x.it = it;
             x.ch = ch;
-            const int tile = blockIdx.x + it * gridDim.x;
-            x.valid = tile < total_tiles;
+            int m_tile = 0, n_tile = 0;
+            x.valid = tile_of(it, m_tile, n_tile);
             x.b = 0, x.t_base = 0, x.n0c = 0, x.ncols = 0, x.last = true, x.step = 0, x.n0 = 0, x.skip = false;
             if (x.valid) {
-                const int n_tile = tile % p.n_tiles;
-                const int m_tile = tile / p.n_tiles;
                 x.b = m_tile / p.tiles_per_batch;
                 x.t_base = (m_tile - x.b * p.tiles_per_batch) * BM + lg * 32;
+                if (x.b >= p.B) x.b = 0, x.t_base = p.T;      // pair: the M tile past the end is never stored
                 const int n0 = n_tile * BN;
                 x.n0 = n0;
                 x.ncols = min(BN, p.epi.N - n0);
@@ -1022,6 +1048,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (mc) cluster_sync_all();        // no CTA leaves while its peer may still multicast into it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
@@ -1177,6 +1204,35 @@ static int launch_tc_epi(const TcParams& p, int m_tiles, cudaStream_t stream) {
         attr_set = true;
     }
     const int tiles = m_tiles * p.n_tiles;
+    if (p.mc) {         // CTA pairs: one cluster of 2 per pair of M tiles
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(kNumSMs & ~1), cfg.blockDim = dim3(kTcThreads), cfg.dynamicSmemBytes = S::TOTAL, cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+        cfg.attrs = at, cfg.numAttrs = 1;
+        // a persistent grid must be co-resident: pairs the GPU can actually host at once (GPCs with an odd number of
+        // usable SMs leave one SM without a partner)
+        static int max_pairs = 0;
+        if (max_pairs == 0) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN, STAGES, EPI>, &cfg) != cudaSuccess || n < 1) n = 1;
+            max_pairs = n;
+        }
+        const int grid = 2 * (p.pair_tiles < max_pairs ? p.pair_tiles : max_pairs);
+        cfg.gridDim = dim3(grid);
+#ifdef SVC_TRACE
+        static bool said = false;
+        if (!said) fprintf(stderr, "seedvc_b200 trace: CTA pairs: max active clusters %d, grid %d\n", max_pairs, grid), said = true;
+#endif
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, EPI>, p);
+        if (e != cudaSuccess) {
+            svc_set_error(cudaGetErrorString(e));
+            return SVC_ERR_CUDA;
+        }
+        return SVC_OK;
+    }
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
     gemm_tc_kernel<BN, STAGES, EPI><<<grid, kTcThreads, S::TOTAL, stream>>>(p);
     SVC_CHECK_LAUNCH();
@@ -1379,6 +1435,27 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
         return SVC_ERR_ARG;
     }
     const int m_tiles = d.B * p.tiles_per_batch;
+    // CTA pairs with the weight tile multicast (wide tiles on the row-layout epilogues, enough M tiles to pair up).
+    // Built, parity-green (tests/test_gpu_kernels.py::test_gemm_cta_pairs ran on it) and measured NEUTRAL: qkv 285 vs
+    // 278 us, plain 235 vs 240 us with 74 co-resident pairs - the K = 512 mainloop already runs at the measured tensor
+    // peak (5 100-5 700 cycles per 128 x 256 x 512 tile = 1.6 PFLOP/s), what is lost is the MMA / epilogue overlap, not
+    // L2 -> SM operand bandwidth.  Compiled in, switched on only by -DSVC_MC_PAIRS experiment builds.
+#ifdef SVC_MC_PAIRS
+    static const int no_mc = svc_env_flag("SVC_NO_MC") ? 1 : 0;
+#else
+    static const int no_mc = 1;
+#endif
+    if (!no_mc && BN == 256 && p.direct && p.store_mode != 0 && m_tiles >= 16) {
+        bool ok = true;
+        for (int i = 0; i < kMaxMaps && ok; ++i) {
+            const int iw = i < n_w ? i : 0;
+            ok = encode_bf16_map(&p.wmap_h[i], wkeys[iw].base, wkeys[iw].K, wkeys[iw].rows, wkeys[iw].rs, 1, 0, BN / 2);
+        }
+        if (ok) {
+            p.mc = 1;
+            p.pair_tiles = ((m_tiles + 1) / 2) * p.n_tiles;
+        }
+    }
     switch (BN) {
         case 32: return launch_tc<32, 8>(p, m_tiles, stream);
         case 64: return launch_tc<64, 8>(p, m_tiles, stream);

@@ -218,6 +218,23 @@ def test_gemm_folded_rms_norm(mode, D, T):
             ops.gemm([(h16, 0, Wp.new_zeros(D, D))], D, B=B, T=T, out_op=h16.clone(), row_scale=(ss, D, 1e-5))
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp16"])
+def test_gemm_cta_pairs(mode):
+    """Shapes of the CTA-pair path (256-column tiles, >= 16 M tiles; cluster of 2, each CTA TMA-loads half of the
+    weight tile and multicasts it - an -DSVC_MC_PAIRS experiment build, measured neutral, see gemm.cu): every
+    row-layout epilogue, even and odd M-tile counts (the odd one computes a tile past the end that must never be
+    stored), several N tiles, k-tap segments, ragged batch rows.  The default build runs the same shapes unpaired."""
+    for T in (2200, 2100, 2049):           # 18, 17 and 17 M tiles (flattened: B = 1)
+        run_gemm_case(mode, False, 1, T, 512, [128], bias=True, out_kind="op")
+        run_gemm_case(mode, False, 1, T, 768, [128], rope=True, out_kind="op")
+        run_gemm_case(mode, False, 1, T, 512, [128], bias=True, inplace=True, out_kind="f32")
+        run_gemm_case(mode, False, 1, T, 1024, [128], act=2, out_kind="op")
+        run_gemm_case(mode, False, 1, T, 512, [128], rowbias=True, act=3, out_kind="op")
+        run_gemm_case(mode, False, 1, T, 512, [192], bias=True, inplace=True, out_kind="both")
+    run_gemm_case(mode, False, 3, 700, 512, [128, 64], bias=True, out_kind="op")        # 3 x 6 tiles, two segments
+    run_gemm_case(mode, False, 2, 1100, 256, [128] * 3, shifts=[-2, 0, 2], bias=True, share_a=True, out_kind="f32")
+
+
 def test_gemm_conv_taps_share_weight_buffer():
     """Taps taken as slices of one (k, N, K) tensor (one TMA map, row offsets)."""
     ops, emu = ops_for("bf16"), EmuOps()
