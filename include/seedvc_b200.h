@@ -173,6 +173,11 @@ int svc_snake_conv_post(const float* x, const float* a, const float* inv_b, cons
                         const float* bias, float* out, int B, int L, int C, int ksize,
                         int use_tanh, int precise, void* stream);
 
+/* conv_post + clamp / tanh alone, on an already activated 16-bit (B, L, C) tensor (svc_snake_aa's output): the
+ * 16-bit modes run activation_post on the tensor cores and this kernel behind it.  w (ksize, C) fp32, bias or NULL. */
+int svc_conv_post(const void* act, int act_dtype, const float* w, const float* bias, float* out, int B, int L,
+                  int C, int ksize, int use_tanh, void* stream);
+
 /* ---------------------------------------------------------------------------
  * svc_cfg_euler: x += dt * (c0 v[0] + c1 v[1] + c2 v[2]); rows t < prompt_len and rows
  * t >= x_lens[b] are set to 0; optionally also writes x in the operand dtype.

@@ -117,6 +117,7 @@ SIGNATURES = {
     "svc_norm_mod_copy": [c_vp, c_ll, c_ll, c_vp, c_vp, c_vp, c_float, c_int, c_vp, c_vp, c_ll, c_ll, c_int,
                           c_int, c_int, c_int, c_int, c_vp],
     "svc_snake_aa": [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp],
+    "svc_conv_post": [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     "svc_snake_conv_post": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_vp],
     "svc_cfg_euler": [c_vp, c_vp, c_int, c_float, c_float, c_float, c_float, c_int, c_int, c_int,

@@ -293,7 +293,8 @@ class BigVGAN(nn.Module):
 
     def launches_per_call(self):
         n_st = len(self.h.upsample_rates)
-        return 2 + n_st * (1 + self.num_kernels * len(self.h.resblock_dilation_sizes[0]) * 4) + 1
+        split_post = self.mode != "fp32" and (self.h.upsample_initial_channel // (2 ** n_st)) % 8 == 0
+        return 2 + n_st * (1 + self.num_kernels * len(self.h.resblock_dilation_sizes[0]) * 4) + 1 + int(split_post)
 
     @torch.no_grad()
     def forward(self, x):
@@ -363,5 +364,10 @@ class BigVGAN(nn.Module):
                                  out_op=nxt_op.view(vw) if (j == nk - 1 and nxt_op is not None) else None)
             cur, cur_op = nxt, nxt_op
         out = torch.empty(B, L, dtype=f32, device=dev)
-        ops.snake_conv_post(cur, *w["post_a"], w["post_w"], w["post_b"], out, self.use_tanh_at_final)
+        if od != f32 and cur.shape[2] % 8 == 0:
+            # activation_post on the tensor cores (16-bit out), conv_post + clamp behind it
+            ops.snake(cur, act, *w["post_a"])
+            ops.conv_post(act, w["post_w"], w["post_b"], out, self.use_tanh_at_final)
+        else:
+            ops.snake_conv_post(cur, *w["post_a"], w["post_w"], w["post_b"], out, self.use_tanh_at_final)
         return out.view(B, 1, L)

@@ -389,6 +389,10 @@ extern "C" int svc_bigvgan_forward(const svc_bigvgan_weights* w, const float* me
         cur_op = nxt_op;
         I = O;
     }
+    if (od != SVC_F32 && I % 8 == 0) {   // activation_post on the tensor cores (16-bit out), conv_post + clamp behind it
+        RUN(svc_snake_aa(nxt, SVC_F32, act, od, w->post_a, w->post_inv_b, B, static_cast<int>(L), I, 0, stream));
+        return svc_conv_post(act, od, w->post_w, w->post_b, out, B, static_cast<int>(L), I, w->post_k, w->use_tanh, stream);
+    }
     return svc_snake_conv_post(nxt, w->post_a, w->post_inv_b, w->post_w, w->post_b, out, B, static_cast<int>(L), I,
                                w->post_k, w->use_tanh, w->precise, stream);
 }

@@ -594,6 +594,60 @@ __global__ void __launch_bounds__(256) snake_conv_post_kernel(
     }
 }
 
+// conv_post on an already activated 16-bit (B, L, C) tensor (the tensor-core Snake's output): C -> 1 channel,
+// ksize taps, zero padding, clamp / tanh.  One thread per output sample; the block stages its (TL + ksize - 1) x C
+// rows with 16-byte loads and every thread walks its ksize rows with 16-byte shared-memory reads (row stride
+// C * 2 = 48 bytes for C = 24: conflict-free per quarter warp).  Reference: modules/bigvgan/bigvgan.py:380-384.
+template <typename TI>
+__global__ void __launch_bounds__(256) conv_post_kernel(const TI* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out, int L,
+                                                        int C, int ksize, int use_tanh) {
+    constexpr int TL = 256;
+    extern __shared__ __align__(16) unsigned char cps[];
+    const int half = ksize / 2;
+    const int rows = TL + 2 * half;
+    const int rb = C * 2;                                  // bytes per row, multiple of 16 (C % 8 == 0)
+    float* ws = reinterpret_cast<float*>(cps + ((rows * rb + 15) & ~15));
+    const int b = blockIdx.y;
+    const int l0 = blockIdx.x * TL;
+    const unsigned char* xb = reinterpret_cast<const unsigned char*>(x + static_cast<long long>(b) * L * C);
+    const int chunks = rb / 16;
+    for (int i = threadIdx.x; i < rows * chunks; i += 256) {
+        const int r = i / chunks, c = i - r * chunks;
+        const int l = l0 - half + r;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);              // zero padding of the conv
+        if (l >= 0 && l < L) v = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(l) * rb) + c);
+        *reinterpret_cast<uint4*>(cps + r * rb + c * 16) = v;
+    }
+    for (int i = threadIdx.x; i < ksize * C; i += 256) ws[i] = w[i];
+    __syncthreads();
+    const int n = l0 + threadIdx.x;
+    if (n >= L) return;
+    float acc = bias != nullptr ? bias[0] : 0.f;
+    for (int k = 0; k < ksize; ++k) {
+        const uint4* row = reinterpret_cast<const uint4*>(cps + (threadIdx.x + k) * rb);
+        const float* wk = ws + k * C;
+        for (int c = 0; c < chunks; ++c) {
+            const uint4 q = row[c];
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float lo, hi;
+                if constexpr (std::is_same<TI, __half>::value) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[j]));
+                    lo = f.x, hi = f.y;
+                } else {
+                    lo = __uint_as_float(u[j] << 16), hi = __uint_as_float(u[j] & 0xffff0000u);
+                }
+                acc = fmaf(wk[c * 8 + 2 * j], lo, acc);
+                acc = fmaf(wk[c * 8 + 2 * j + 1], hi, acc);
+            }
+        }
+    }
+    acc = use_tanh ? tanhf(acc) : fminf(fmaxf(acc, -1.0f), 1.0f);
+    out[static_cast<long long>(b) * L + n] = acc;
+}
+
 template <typename TI, typename TO, int CT, int LPT, bool PRECISE>
 static void launch_snake2(const TI* xi, TO* o, const float* a, const float* inv_b, int B, int L, int C,
                           cudaStream_t st) {
@@ -706,6 +760,31 @@ extern "C" int svc_snake_aa(const void* x, int x_dtype, void* out, int out_dtype
 #undef SNAKE_DISPATCH
     svc_set_error("svc_snake_aa: unsupported dtype");
     return SVC_ERR_UNSUPPORTED;
+}
+
+extern "C" int svc_conv_post(const void* act, int act_dtype, const float* w, const float* bias, float* out, int B, int L,
+                             int C, int ksize, int use_tanh, void* stream) {
+    if (B < 1 || L < 1 || C < 8 || C % 8 != 0 || C > 256 || ksize < 1 || ksize > 15 || (ksize % 2) == 0 || B > 65535 ||
+        (act_dtype != SVC_F16 && act_dtype != SVC_BF16) || reinterpret_cast<uintptr_t>(act) % 16 != 0) {
+        svc_set_error("svc_conv_post: 16-bit (B, L, C) input, C % 8 == 0, C <= 256, odd ksize <= 15, 16-byte aligned");
+        return SVC_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rows = 256 + 2 * (ksize / 2);
+    const int smem = ((rows * C * 2 + 15) & ~15) + ksize * C * 4;
+    dim3 grid((L + 255) / 256, B);
+    if (act_dtype == SVC_F16) {
+        static bool attr = false;
+        if (!attr) cudaFuncSetAttribute(conv_post_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), attr = true;
+        conv_post_kernel<__half><<<grid, 256, smem, st>>>(static_cast<const __half*>(act), w, bias, out, L, C, ksize, use_tanh);
+    } else {
+        static bool attr = false;
+        if (!attr) cudaFuncSetAttribute(conv_post_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024), attr = true;
+        conv_post_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(act), w, bias, out, L, C,
+                                                                 ksize, use_tanh);
+    }
+    SVC_CHECK_LAUNCH();
+    return SVC_OK;
 }
 
 extern "C" int svc_snake_conv_post(const float* x, const float* a, const float* inv_b, const float* w,

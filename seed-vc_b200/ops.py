@@ -266,6 +266,16 @@ class Ops:
                                     self.precise, self._stream()), "svc_snake_aa")
         self._t1()
 
+    def conv_post(self, act, w, bias, out, use_tanh):
+        """act (B, L, C) 16-bit (already activated) -> out (B, L) fp32; w (k, C) fp32."""
+        self._chk(act, w, bias, out)
+        B, L, Cc = act.shape
+        assert act.is_contiguous() and out.shape == (B, L) and out.is_contiguous() and w.shape[1] == Cc
+        self._t0("snake_conv_post", 0.0, float(B) * L * (Cc * 2 + 4))
+        check(self.lib.svc_conv_post(act.data_ptr(), self._code(act.dtype), w.data_ptr(), _ptr(bias), out.data_ptr(),
+                                     B, L, Cc, w.shape[0], int(bool(use_tanh)), self._stream()), "svc_conv_post")
+        self._t1()
+
     def snake_conv_post(self, x, a, inv_b, w, bias, out, use_tanh):
         """x (B, L, C) fp32 -> out (B, L) fp32; w (k, C) fp32."""
         self._chk(x, a, inv_b, w, bias, out)

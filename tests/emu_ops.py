@@ -129,6 +129,13 @@ class EmuOps:
         self.launches += 1
         out.copy_(self._snake(x, a, inv_b))
 
+    def conv_post(self, act, w, bias, out, use_tanh):
+        self.launches += 1
+        y = act.float().transpose(1, 2)                               # (B, C, L)
+        k = w.shape[0]
+        o = F.conv1d(y, w.t().unsqueeze(0), bias, padding=k // 2)[:, 0]
+        out.copy_(torch.tanh(o) if use_tanh else o.clamp(-1.0, 1.0))
+
     def snake_conv_post(self, x, a, inv_b, w, bias, out, use_tanh):
         self.launches += 1
         y = self._snake(x, a, inv_b).transpose(1, 2)                  # (B, C, L)

@@ -376,6 +376,25 @@ def test_snake_tensor_core_sequence_ends(C, mode):
         assert rel_l2(out.float(), ref) < (6e-4 if mode == "fp16" else 4e-3), L
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("use_tanh", [False, True])
+@pytest.mark.parametrize("C,k,L", [(24, 7, 700), (32, 7, 255), (24, 3, 5), (64, 15, 1030)])
+def test_conv_post(dtype, use_tanh, C, k, L):
+    """svc_conv_post: C -> 1 conv + clamp / tanh on a 16-bit activated tensor (bigvgan.py:380-384), zero padding at
+    both sequence ends, block boundaries."""
+    ops, emu = ops_for("fp16"), EmuOps()
+    B = 3
+    act = rnd(B, L, C, seed=L, dtype=dtype)
+    w = rnd(k, C, seed=4, scale=0.3)
+    bias = rnd(1, seed=5)
+    for bb in (None, bias):
+        out, ref = torch.full((B, L), 9.0, device=DEV), torch.zeros(B, L, device=DEV)
+        ops.conv_post(act, w, bb, out, use_tanh)
+        emu.conv_post(act, w, bb, ref, use_tanh)
+        assert float((out - ref).abs().max()) < 2e-5
+        assert float(out.abs().max()) <= 1.0
+
+
 def test_snake_known_answer():
     """SURVEY section 8c KAT: SnakeBeta(4, logscale, alpha=beta=0) on arange(40)/10."""
     ops = ops_for("fp32")
