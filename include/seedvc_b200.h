@@ -108,9 +108,8 @@ typedef struct svc_gemm_desc {
        caller folds g into the weight columns and a W^T into `bias`, the GEMM that PRODUCES x reports the row sums of
        squares and the GEMM that CONSUMES x scales its accumulator rows.
        row_ss_out: (B*T, SVC_SS_SLOTS) fp32, contiguous, zeroed once by the caller.  Two-output tensor-core calls
-         (out_f32 + out_op) write, per output row, partial sums of squares of the final fp32 values (two per N tile,
-         one per epilogue warp group) into the leading slots; untouched slots keep their zeros.  N % 32 == 0, at most
-         SVC_SS_SLOTS / 2 N tiles.
+         (out_f32 + out_op) write, per output row, the sum of squares of the final fp32 values of every N tile into
+         the leading slots (untouched slots keep their zeros).  N % 32 == 0, at most SVC_SS_SLOTS N tiles.
        row_ss_in: the same array from an earlier call: acc[r,:] *= rsqrt(sum(slots[r]) * rs_inv_dim + rs_eps) before
          the bias.  Tensor-core calls with bias + (RoPE | SwiGLU pair) -> out_op only.
        NULL = off.  Not available on the SIMT / fp32 path (SVC_ERR_UNSUPPORTED). */

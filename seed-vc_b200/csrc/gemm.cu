@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         }
         for (int a = 0; a < 4; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], kEpiWarps);      // every epilogue warp reads a share of every tile
+            mbar_init(&tmem_empty_bar[a], kEpiWarps / 2);
         }
         for (int a = 0; a < 2 * kEpiWarps; ++a) mbar_init(&res_bar[a], 1);
         if (EPI == 5 && p.res_tma) tma_prefetch_desc(&p.rmap);
@@ -848,22 +848,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         constexpr int acc_per_item = pair ? 64 : 32;   // accumulator columns per work item
         struct Item {
             int it, ch, b, t_base, n0c, ncols, step, n0;
-            bool valid, last, skip;
+            bool valid, last;
         };
-        // Both groups work on EVERY tile: group g takes the column chunks g, g + 2, g + 4, ... of the tile.  The
-        // accumulator buffer is then released after HALF the epilogue time of a tile, which is what lets the MMA of
-        // tile i + 2 (same buffer) overlap the epilogue of tile i + 1: with one group per tile a buffer stayed busy
-        // for MMA + the whole epilogue (5 000 + 11 000 cycles for a K = 512, 128 x 256 tile, clock stamps) and the
-        // tensor pipe idled half the time.  Chunks two apart are 64 columns apart, so consecutive RoPE items of a
-        // warp use the same 16 (cos, sin) pairs and the table is read once per tile and warp.
-        auto group_items = [&](int ncols) { return ((ncols + acc_per_item - 1) / acc_per_item + 1 - group) >> 1; };
+        // Tiles alternate between the two groups.  (Measured alternative: both groups sharing every tile, group g taking
+        // the column chunks g, g + 2, ... so the accumulator buffer is released after half the epilogue time: qkv 283 ->
+        // 275 us isolated, but 42.8 vs 42.2 ms per Euler step in situ at the power-capped clock, and ~40 spilled
+        // registers in the epilogue warps - not kept.)
+        // RoPE items of a full tile are visited even chunks first, then odd ones: chunks 64 columns apart
+        // use the same 16 (cos, sin) pairs, so the table is read twice per tile instead of once per chunk
+        const bool rope_order = direct && !pair && p.epi.act == SVC_ACT_ROPE;
+        auto chunk_of = [&](int step, int ncols) {
+            const int n = ncols / acc_per_item;
+            if (!rope_order || ncols != BN || (n & 1)) return step;
+            return step < n / 2 ? 2 * step : 2 * (step - n / 2) + 1;
+        };
         auto make_item = [&](int it, int ch) {          // full (re)computation: once per tile
             Item x;
             x.it = it;
             x.ch = ch;
             int m_tile = 0, n_tile = 0;
             x.valid = tile_of(it, m_tile, n_tile);
-            x.b = 0, x.t_base = 0, x.n0c = 0, x.ncols = 0, x.last = true, x.step = 0, x.n0 = 0, x.skip = false;
+            x.b = 0, x.t_base = 0, x.n0c = 0, x.ncols = 0, x.last = true, x.step = 0, x.n0 = 0;
             if (x.valid) {
                 x.b = m_tile / p.tiles_per_batch;
                 x.t_base = (m_tile - x.b * p.tiles_per_batch) * BM + lg * 32;
@@ -871,22 +876,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 const int n0 = n_tile * BN;
                 x.n0 = n0;
                 x.ncols = min(BN, p.epi.N - n0);
-                const int count = group_items(x.ncols);   // chunks of this group in this tile
                 x.step = 0;
-                x.ch = group;
+                x.ch = chunk_of(0, x.ncols);
                 x.n0c = n0 + x.ch * acc_per_item;
-                x.last = count <= 1;
-                x.skip = count == 0;                    // narrow tile: nothing for this group, but it still takes
-            }                                           // part in the buffer hand-over (full wait, empty arrive)
+                x.last = acc_per_item >= x.ncols;
+            }
             return x;
         };
         auto next_item = [&](const Item& c) {           // within a tile: no divisions
-            if (c.last) return make_item(c.it + 1, 0);
+            if (c.last) return make_item(c.it + 2, 0);
             Item x = c;
             x.step = c.step + 1;
-            x.ch = 2 * x.step + group;
+            x.ch = chunk_of(x.step, c.ncols);
             x.n0c = c.n0 + x.ch * acc_per_item;
-            x.last = x.step + 1 >= group_items(c.ncols);
+            x.last = (x.step + 1) * acc_per_item >= c.ncols;
             return x;
         };
         // geometry used by the prefetch (4 columns per lane, 8 steps) in TMA mode
@@ -895,7 +898,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         // the item loop, specialised on the epilogue kind (see epilogue_item_direct); EK != 0 only for direct EPIs
         auto run_items = [&](auto ek_tag) {
         constexpr int EK = decltype(ek_tag)::value;
-        Item cur = make_item(0, 0);
+        Item cur = make_item(group, 0);
         EpiChunk g_cur = g_tma;
         if constexpr (tma_mode) g_cur.c0 = pair ? (cur.n0c >> 1) : cur.n0c;
         else g_cur = epi_chunk_geom(p.epi, cur.n0c);
@@ -906,9 +909,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         constexpr bool rs_in = EK == EK_RS_ROPE || EK == EK_RS_SWIGLU;
         const bool ss_out = EPI == 5 && p.epi.row_ss_out != nullptr;
         float rs_row = 1.0f, ss_acc = 0.f;
-        if (cur.valid && !cur.skip && want_prefetch && g_cur.vec && cur.t_base < p.T)
+        if (cur.valid && want_prefetch && g_cur.vec && cur.t_base < p.T)
             epi_prefetch(p.epi, g_cur, lane, cur.b, cur.t_base, p.T, rr_cur);
-        if (rope_direct && cur.valid && !cur.skip && cur.n0c < p.epi.rope_cols)
+        if (rope_direct && cur.valid && cur.n0c < p.epi.rope_cols)
             rope_prefetch_rows(p.epi, cur.n0c, lane, cur.t_base, rr_cur);
         const bool res_any = EK == EK_GENERIC ? (direct && !pair && p.res_rows)
                                               : ((EK == EK_BIAS || EK == EK_RES) && EPI == 5 && p.res_rows);
@@ -921,11 +924,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             tma_load_3d(reinterpret_cast<uint8_t*>(stage_buf) + (r_issued & 1) * 4096, &p.rmap, &rbar[r_issued & 1],
                         x.n0c, x.t_base, x.b);
         };
-        if (res_tma && cur.valid && !cur.skip && cur.t_base < p.T) {
+        if (res_tma && cur.valid && cur.t_base < p.T) {
             if (lane == 0) res_issue(cur);
             ++r_issued;
         }
-        if (res_direct && cur.valid && !cur.skip) res_prefetch_rows(p.epi, cur.n0c, lane, cur.b, cur.t_base, p.T, rr_cur);
+        if (res_direct && cur.valid) res_prefetch_rows(p.epi, cur.n0c, lane, cur.b, cur.t_base, p.T, rr_cur);
         int tr_i = 0;
         const bool tr_on = (warp == 2 && lane == 0);
         while (cur.valid) {
@@ -946,12 +949,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
             }
             uint32_t r[32], r2[pair ? 32 : 1];
             const uint32_t taddr = taddr0 + (cur.it % NB) * ACC_COLS;
-            if (!cur.skip) {
-                tmem_ld_32x32(taddr + cur.ch * acc_per_item, r);
-                if constexpr (pair) tmem_ld_32x32(taddr + cur.ch * 64 + 32, r2);
-            }
-            Item nxt = next_item(cur);
-            const bool nxt_on = nxt.valid && !nxt.skip;
+            tmem_ld_32x32(taddr + cur.ch * acc_per_item, r);
+            if constexpr (pair) tmem_ld_32x32(taddr + cur.ch * 64 + 32, r2);
+            const Item nxt = next_item(cur);
+            const bool nxt_on = nxt.valid;
             EpiChunk g_nxt = g_tma;
             if constexpr (tma_mode) g_nxt.c0 = pair ? (nxt.n0c >> 1) : nxt.n0c;
             else g_nxt = epi_chunk_geom(p.epi, nxt.n0c);
@@ -982,7 +983,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[cur.it % NB]);
             }
-            if (cur.t_base < p.T && !cur.skip && !(SVC_DBG_BITS(p) & 1)) {
+            if (cur.t_base < p.T && !(SVC_DBG_BITS(p) & 1)) {
                 if constexpr (EPI == 0) {
                     float v[32];
 #pragma unroll
@@ -1008,7 +1009,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                             if (cur.last) {
                                 const int t = cur.t_base + lane;
                                 if (t < p.T)
-                                    p.epi.row_ss_out[(static_cast<long long>(cur.b) * p.T + t) * SVC_SS_SLOTS + 2 * (cur.n0 / BN) + group] = ss_acc;
+                                    p.epi.row_ss_out[(static_cast<long long>(cur.b) * p.T + t) * SVC_SS_SLOTS + cur.n0 / BN] = ss_acc;
                                 ss_acc = 0.f;
                             }
                         }
@@ -1426,7 +1427,7 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
             return SVC_ERR_UNSUPPORTED;
         }
     }
-    if (d.row_ss_out != nullptr && !(p.dual && d.N % 32 == 0 && 2 * p.n_tiles <= SVC_SS_SLOTS)) {
+    if (d.row_ss_out != nullptr && !(p.dual && d.N % 32 == 0 && p.n_tiles <= SVC_SS_SLOTS)) {
         svc_set_error("svc_gemm: row_ss_out needs the two-output tensor-core epilogue, N % 32 == 0 and <= 4 N tiles");
         return SVC_ERR_UNSUPPORTED;
     }
