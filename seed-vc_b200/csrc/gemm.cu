@@ -56,6 +56,7 @@ struct alignas(64) TcParams {
     int res_rows;              // direct: residual read in the row layout (one 128 B line per thread)
     int dual;                  // direct: fp32 tile -> out_f32 (omap) AND bf16 tile -> out_op (omap2)
     int res_tma;               // dual: the residual item is TMA-loaded into the staging tile (rmap), not read by LSU
+    int epi5;                  // run the two-staging-tile epilogue (EPI 5): dual, or one fp32 output + TMA residual
     CUtensorMap rmap;          // (N_out, T, B) view of the residual, same box / swizzle as omap
     CUtensorMap omap2;
     CUtensorMap omap;          // (N_out, T, B) view of the output, box {32, 32, 1}; swizzled when direct
@@ -628,7 +629,7 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     if (lane == 0) bulk_wait_read0();
     __syncwarp();
     uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
-    if (p.store_mode == 1 || DUAL) {
+    if (p.store_mode == 1 || (DUAL && p.dual)) {
         uint8_t* row = sb + (DUAL ? kDualOpOff : 0) + lane * 64;
         const int sw = (lane >> 1) & 3;
         if (e.op_is_f16) {         // warp-uniform: one conversion flavour per launch
@@ -658,7 +659,7 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     if (lane == 0) {
         if (p.store_mode == 2) tma_reduce_add_3d(&p.omap, fbuf, c0, t_base, b);
         else tma_store_3d(&p.omap, fbuf, c0, t_base, b);
-        if (DUAL) tma_store_3d(&p.omap2, sb + kDualOpOff, c0, t_base, b);
+        if (DUAL && p.dual) tma_store_3d(&p.omap2, sb + kDualOpOff, c0, t_base, b);
         bulk_commit();
     }
 }
@@ -1248,7 +1249,7 @@ static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
         if (pair) return p.direct ? launch_tc_epi<BN, STAGES, 4>(p, m_tiles, stream)
                                   : launch_tc_epi<BN, STAGES, 2>(p, m_tiles, stream);
     }
-    if (p.dual) return launch_tc_epi<BN, epi5_stages(BN, STAGES), 5>(p, m_tiles, stream);
+    if (p.epi5) return launch_tc_epi<BN, epi5_stages(BN, STAGES), 5>(p, m_tiles, stream);
     return p.direct ? launch_tc_epi<BN, STAGES, 3>(p, m_tiles, stream)
                     : launch_tc_epi<BN, STAGES, 1>(p, m_tiles, stream);
 }
@@ -1401,9 +1402,17 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
     }
     // two outputs (fp32 stream + bf16 operand copy), optionally with a residual read in the row layout
     const bool pair_act = d.act == SVC_ACT_SWIGLU_PAIR || d.act == SVC_ACT_TANH_SIG_PAIR;
+    // ... or one fp32 output with a residual that is NOT the output itself (BigVGAN conv2 of an AMP pair, the hoisted
+    // merge constants): the residual items come in by TMA, so this beats the transposing LSU epilogue (EPI 0) it used
+    // to fall back to
+#ifdef SVC_NO_RES_F32_DIRECT
+    const bool res_f32_direct = false;
+#else
+    const bool res_f32_direct = d.res != nullptr && !no_res_tma;
+#endif
     if (p.store_mode == 0 && p.direct && p.epi.vec_ok && !no_tma_store && !pair_act &&
         d.act != SVC_ACT_ROPE && d.out_f32 != nullptr && !(d.accumulate && d.out_op != nullptr) &&
-        d.out_op != nullptr) {   // (row-layout residual reads without a second output measured slower than EPI 0)
+        (d.out_op != nullptr || res_f32_direct)) {
         bool ok = encode_out_map(&p.omap, d.out_f32, true, p.epi.N_out, d.T, d.of_rstride, d.B, d.of_bstride, true);
         if (ok && d.out_op != nullptr)
             ok = encode_out_map(&p.omap2, d.out_op, false, p.epi.N_out, d.T, d.oo_rstride, d.B, d.oo_bstride, true);
@@ -1414,6 +1423,8 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
             // residual items by TMA (same box and swizzle as the fp32 output tile they are finished in)
             p.res_tma = d.res != nullptr && !no_res_tma &&
                         encode_out_map(&p.rmap, d.res, true, p.epi.N_out, d.T, d.res_rstride, d.B, d.res_bstride, true);
+            p.epi5 = 1;
+            if (!p.dual && !p.res_tma) p.store_mode = 0, p.res_rows = 0, p.epi5 = 0;   // nothing gained: transposing epilogue
         }
     }
     if (BN < 64 && pair_act) p.store_mode = 0;
