@@ -1447,6 +1447,24 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
         return SVC_ERR_ARG;
     }
     const int m_tiles = d.B * p.tiles_per_batch;
+#ifdef SVC_TRACE
+    if (getenv("SVC_LOG_PATHS") != nullptr) {    // which epilogue every distinct call shape takes (trace builds only)
+        static unsigned long long seen[256];
+        static int n_seen = 0;
+        const unsigned long long key = (static_cast<unsigned long long>(d.N) << 40) ^ (static_cast<unsigned long long>(total_kb) << 24) ^
+                                       (p.store_mode << 20) ^ (p.direct << 19) ^ (p.dual << 18) ^ (p.res_rows << 17) ^ (p.res_tma << 16) ^
+                                       (d.act << 8) ^ (d.bias != nullptr) ^ ((d.rowbias != nullptr) << 1) ^ ((d.gate != nullptr) << 2) ^
+                                       ((d.accumulate != 0) << 3) ^ ((d.alpha != 1.0f) << 4);
+        bool found = false;
+        for (int i = 0; i < n_seen; ++i) found |= seen[i] == key;
+        if (!found && n_seen < 256) {
+            seen[n_seen++] = key;
+            fprintf(stderr, "svc_gemm path: N %d kblocks %d BN %d rows %lld | store_mode %d direct %d dual %d res_rows %d res_tma %d epi5 %d | act %d bias %d rowbias %d gate %d acc %d alpha %g out_f32 %d out_op %d\n",
+                    d.N, total_kb, BN, static_cast<long long>(d.B) * d.T, p.store_mode, p.direct, p.dual, p.res_rows, p.res_tma, p.epi5, d.act,
+                    d.bias != nullptr, d.rowbias != nullptr, d.gate != nullptr, d.accumulate, d.alpha, d.out_f32 != nullptr, d.out_op != nullptr);
+        }
+    }
+#endif
     // CTA pairs with the weight tile multicast (wide tiles on the row-layout epilogues, enough M tiles to pair up).
     // Built, parity-green (tests/test_gpu_kernels.py::test_gemm_cta_pairs ran on it) and measured NEUTRAL: qkv 285 vs
     // 278 us, plain 235 vs 240 us with 74 co-resident pairs - the K = 512 mainloop already runs at the measured tensor
