@@ -31,8 +31,9 @@ for line in out.splitlines():
                 total[o] += 1
 print("# SASS opcode histogram of `seed-vc_b200/libseedvc_b200.so` (sm_100a)\n")
 print("Produced by `scripts/sass_histogram.py` (cuobjdump -sass).  `UTCHMMA` = tcgen05.mma kind::f16, `LDTM`/`STTM` = "
-      "tcgen05.ld/st, `UTMALDG`/`UTMASTG`/`UTMAREDG` = TMA tensor load / store / reduce-add, `HMMA` = legacy mma.sync "
-      "(must be 0).\n")
+      "tcgen05.ld/st, `UTMALDG`/`UTMASTG`/`UTMAREDG` = TMA tensor load / store / reduce-add, `HMMA` = warp-level mma.sync: "
+      "only `snake_mma_kernel` uses it, on purpose (banded-Toeplitz FIRs chained through the accumulator fragment, "
+      "DESIGN section 5); every GEMM / attention kernel must show 0.\n")
 print("Totals: " + ", ".join(f"{total[o]} `{o}`" for o in OPS) + f"; {len(hist)} kernels.\n")
 print("| kernel | instr | " + " | ".join(OPS) + " |")
 print("|---|---:|" + "---:|" * len(OPS))
