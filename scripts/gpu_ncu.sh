@@ -14,8 +14,8 @@ CMD="python bench.py --workload profile --steps 1 --warmup 1 --no-cpu-baseline -
 # launch list of ONE conversion pass of the bench's default command (config 2): our kernels only
 C2="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile"
 $C2 > gpurun_out/ncu_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:svc:: -c ${PASS_LAUNCHES:-3519} --csv --log-file gpurun_out/launches.csv $C2 > gpurun_out/ncu_launches.log 2>&1
-echo "ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:svc:: -c ${PASS_LAUNCHES:-3519} --csv $C2" > gpurun_out/launches.cmd
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:svc:: -c ${PASS_LAUNCHES:-3520} --csv --log-file gpurun_out/launches.csv $C2 > gpurun_out/ncu_launches.log 2>&1
+echo "ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:svc:: -c ${PASS_LAUNCHES:-3520} --csv $C2" > gpurun_out/launches.cmd
 echo "launch list exit $?"
 $CMD > gpurun_out/ncu_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 100 -c 6 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
