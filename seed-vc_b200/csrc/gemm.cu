@@ -57,6 +57,7 @@ struct alignas(64) TcParams {
     int dual;                  // direct: fp32 tile -> out_f32 (omap) AND bf16 tile -> out_op (omap2)
     int res_tma;               // dual: the residual item is TMA-loaded into the staging tile (rmap), not read by LSU
     int epi5;                  // run the two-staging-tile epilogue (EPI 5): dual, or one fp32 output + TMA residual
+    int wide;                  // 16-bit-only output in items of 64 columns (EPI 7): omap box is {64, 32}, SWIZZLE_128B
     CUtensorMap rmap;          // (N_out, T, B) view of the residual, same box / swizzle as omap
     CUtensorMap omap2;
     CUtensorMap omap;          // (N_out, T, B) view of the output, box {32, 32, 1}; swizzled when direct
@@ -664,6 +665,97 @@ __device__ __forceinline__ void epilogue_item_direct(const TcParams& p, float* s
     }
 }
 
+// 16-bit-only output, 64 columns per item (EPI 7): the same row-layout epilogue with HALF as many items per tile.
+// The per-item fixed costs (wait for the previous store's smem read, proxy fence, TMA issue, item bookkeeping) are
+// what an epilogue warp alone on its scheduler slot spends its time on: the SwiGLU-pair epilogue, which always had
+// 64 accumulator columns per item, reached 1 285 TFLOP/s on w13 where the 32-column RoPE / bias / plain items of wqkv
+// stayed at 970 - 1 090 with half the FLOPs per tile.  Staging tile: 32 rows x 128 B, SWIZZLE_128B (box {64, 32}).
+// RoPE: one item = one head, so the row's 32 (cos, sin) pairs are the same for every item of a tile (L1 hits after
+// the first); they are read in two halves right where they are used instead of being carried in registers.
+template <int EK>
+__device__ __forceinline__ void epilogue_item_wide(const TcParams& p, float* stage, int lane, int b, int t_base,
+                                                   int c0, float (&v)[64], int rope_pos) {
+    const EpiParams& e = p.epi;
+    constexpr bool G = EK == EK_GENERIC;
+    const bool has_bias = G ? e.bias != nullptr : EK == EK_BIAS;
+    const bool has_rowbias = G ? e.rowbias != nullptr : false;
+    const bool has_gate = G ? e.gate != nullptr : false;
+    const bool has_alpha = G ? e.alpha != 1.0f : false;
+    const int act = G ? e.act : EK == EK_ROPE ? SVC_ACT_ROPE : SVC_ACT_NONE;
+    if (has_bias) {
+#pragma unroll
+        for (int j = 0; j < 64; j += 4)
+            if (c0 + j < e.N) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(e.bias + c0 + j));
+                v[j] += q.x, v[j + 1] += q.y, v[j + 2] += q.z, v[j + 3] += q.w;
+            }
+    }
+    if (has_rowbias) {
+        const float* rb = e.rowbias + static_cast<long long>(b) * e.rowbias_bstride + c0;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4)
+            if (c0 + j < e.N) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(rb + j));
+                v[j] += q.x, v[j + 1] += q.y, v[j + 2] += q.z, v[j + 3] += q.w;
+            }
+    }
+    if (act == SVC_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = fast_silu(v[j]);
+    } else if (act == SVC_ACT_ROPE && c0 < e.rope_cols) {
+        const float qs = c0 < e.q_cols ? e.q_scale : 1.0f;
+        const float2* tab = reinterpret_cast<const float2*>(e.rope_tab_t) + rope_pos;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float2 cs[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cs[i] = __ldg(tab + static_cast<long long>(16 * h + i) * e.rope_ld);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float x0 = v[32 * h + 2 * i], x1 = v[32 * h + 2 * i + 1];
+                v[32 * h + 2 * i] = (x0 * cs[i].x - x1 * cs[i].y) * qs;
+                v[32 * h + 2 * i + 1] = (x1 * cs[i].x + x0 * cs[i].y) * qs;
+            }
+        }
+    }
+    if (has_gate) {
+        const float* gp = e.gate + static_cast<long long>(b) * e.gate_bstride + c0;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4)
+            if (c0 + j < e.N_out) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(gp + j));
+                v[j] *= q.x, v[j + 1] *= q.y, v[j + 2] *= q.z, v[j + 3] *= q.w;
+            }
+    }
+    if (has_alpha) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] *= e.alpha;
+    }
+    if (lane == 0) bulk_wait_read0();       // the previous TMA store of this warp has read the staging tile
+    __syncwarp();
+    uint8_t* row = reinterpret_cast<uint8_t*>(stage) + lane * 128;
+    const int sw = lane & 7;
+    if (e.op_is_f16) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(row + ((q ^ sw) << 4)) =
+                make_uint4(pack_f16(v[8 * q], v[8 * q + 1]), pack_f16(v[8 * q + 2], v[8 * q + 3]),
+                           pack_f16(v[8 * q + 4], v[8 * q + 5]), pack_f16(v[8 * q + 6], v[8 * q + 7]));
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(row + ((q ^ sw) << 4)) =
+                make_uint4(pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_3d(&p.omap, stage, c0, t_base, b);
+        bulk_commit();
+    }
+}
+
 // Which specialised item loop a launch can use (warp-uniform, evaluated once per kernel)
 __device__ __forceinline__ int epi_kind(const TcParams& p, bool pair, bool dual) {
     const EpiParams& e = p.epi;
@@ -845,8 +937,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);   // + buffer (tile index % NB) * ACC_COLS
         constexpr bool tma_mode = EPI != 0;
         constexpr bool pair = EPI == 2 || EPI == 4;
-        constexpr bool direct = EPI >= 3;          // 3 direct, 4 direct pair, 5 direct with two outputs
-        constexpr int acc_per_item = pair ? 64 : 32;   // accumulator columns per work item
+        constexpr bool wide = EPI == 7;            // 16-bit-only output, 64 columns per item
+        constexpr bool direct = EPI >= 3;          // 3 direct, 4 direct pair, 5 direct with two outputs, 7 direct wide
+        constexpr int acc_per_item = (pair || wide) ? 64 : 32;   // accumulator columns per work item
         struct Item {
             int it, ch, b, t_base, n0c, ncols, step, n0;
             bool valid, last;
@@ -857,7 +950,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         // registers in the epilogue warps - not kept.)
         // RoPE items of a full tile are visited even chunks first, then odd ones: chunks 64 columns apart
         // use the same 16 (cos, sin) pairs, so the table is read twice per tile instead of once per chunk
-        const bool rope_order = direct && !pair && p.epi.act == SVC_ACT_ROPE;
+        const bool rope_order = direct && !pair && !wide && p.epi.act == SVC_ACT_ROPE;
         auto chunk_of = [&](int step, int ncols) {
             const int n = ncols / acc_per_item;
             if (!rope_order || ncols != BN || (n & 1)) return step;
@@ -905,7 +998,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         else g_cur = epi_chunk_geom(p.epi, cur.n0c);
         float4 rr_cur[8], rr_nxt[8];
         const bool want_prefetch = EK == EK_GENERIC && !direct && (!tma_mode || p.epi.act == SVC_ACT_ROPE);
-        const bool rope_direct = EK == EK_GENERIC ? (direct && p.epi.act == SVC_ACT_ROPE) : (EK == EK_ROPE || EK == EK_RS_ROPE);
+        const bool rope_direct = !wide && (EK == EK_GENERIC ? (direct && p.epi.act == SVC_ACT_ROPE) : (EK == EK_ROPE || EK == EK_RS_ROPE));
+        int rope_pos = 0;                                           // wide RoPE: this row's table position, once per tile
         // folded RMS norm: this thread's row scale (consumer) / running sum of squares of its row (producer)
         constexpr bool rs_in = EK == EK_RS_ROPE || EK == EK_RS_SWIGLU;
         const bool ss_out = EPI == 5 && p.epi.row_ss_out != nullptr;
@@ -945,13 +1039,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                                         p.epi.rs_eps);
                     }
                 }
+                if constexpr (wide) {
+                    const int row = cur.t_base + lane;
+                    rope_pos = min(p.epi.rope_pos0 + (p.epi.rope_mod > 0 ? row % p.epi.rope_mod : row), p.epi.rope_ld - 1);
+                }
                 mbar_wait(&tmem_full_bar[cur.it % NB], (cur.it / NB) & 1);
                 tc_fence_after();
             }
-            uint32_t r[32], r2[pair ? 32 : 1];
+            uint32_t r[32], r2[(pair || wide) ? 32 : 1];
             const uint32_t taddr = taddr0 + (cur.it % NB) * ACC_COLS;
             tmem_ld_32x32(taddr + cur.ch * acc_per_item, r);
-            if constexpr (pair) tmem_ld_32x32(taddr + cur.ch * 64 + 32, r2);
+            if constexpr (pair || wide) tmem_ld_32x32(taddr + cur.ch * 64 + 32, r2);
             const Item nxt = next_item(cur);
             const bool nxt_on = nxt.valid;
             EpiChunk g_nxt = g_tma;
@@ -991,6 +1089,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
                     epilogue_chunk_coalesced(p.epi, g_cur, stage_buf, lane, cur.b, cur.t_base, p.T,
                                              cur.n0c, v, rr_cur, SVC_DBG_BITS(p));
+                } else if constexpr (wide) {
+                    float v[64];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]), v[32 + j] = __uint_as_float(r2[j]);
+                    epilogue_item_wide<EK>(p, stage_buf, lane, cur.b, cur.t_base, cur.n0c, v, rope_pos);
                 } else if constexpr (pair) {
                     float v[64];
 #pragma unroll
@@ -1031,10 +1134,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tc_kernel(const __grid_con
         if constexpr (direct) ek = epi_kind(p, pair, EPI == 5);
         if (EPI != 5 && ek == EK_PLAIN) {
             if constexpr (direct && EPI != 5) run_items(std::integral_constant<int, EK_PLAIN>{});
-        } else if (EPI == 3 && ek == EK_ROPE) {
-            if constexpr (EPI == 3) run_items(std::integral_constant<int, EK_ROPE>{});
-        } else if ((EPI == 3 || EPI == 5) && ek == EK_BIAS) {
-            if constexpr (EPI == 3 || EPI == 5) run_items(std::integral_constant<int, EK_BIAS>{});
+        } else if ((EPI == 3 || EPI == 7) && ek == EK_ROPE) {
+            if constexpr (EPI == 3 || EPI == 7) run_items(std::integral_constant<int, EK_ROPE>{});
+        } else if ((EPI == 3 || EPI == 5 || EPI == 7) && ek == EK_BIAS) {
+            if constexpr (EPI == 3 || EPI == 5 || EPI == 7) run_items(std::integral_constant<int, EK_BIAS>{});
         } else if (EPI == 4 && ek == EK_ROWBIAS_TS) {
             if constexpr (EPI == 4) run_items(std::integral_constant<int, EK_ROWBIAS_TS>{});
         } else if (EPI == 5 && ek == EK_RES) {
@@ -1177,7 +1280,7 @@ bool encode_bf16_map(CUtensorMap* map, const void* ptr, int K, long long rows, l
 
 // (N_out, T, B) view of an output tensor for the TMA-store epilogue: box {32, 32, 1}, no swizzle
 static bool encode_out_map(CUtensorMap* map, const void* ptr, bool f32, int n_out, long long rows,
-                           long long rstride, long long batches, long long bstride, bool swizzled) {
+                           long long rstride, long long batches, long long bstride, bool swizzled, int box_cols = 32) {
     EncodeTiledFn fn = get_encode_fn();
     const int es = f32 ? 4 : 2;
     if (fn == nullptr || ptr == nullptr) return false;
@@ -1187,11 +1290,12 @@ static bool encode_out_map(CUtensorMap* map, const void* ptr, bool f32, int n_ou
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(n_out), static_cast<cuuint64_t>(rows),
                           static_cast<cuuint64_t>(batches)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(rstride * es), static_cast<cuuint64_t>(bstride * es)};
-    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    !swizzled ? CU_TENSOR_MAP_SWIZZLE_NONE : f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    !swizzled ? CU_TENSOR_MAP_SWIZZLE_NONE
+                              : (f32 || box_cols == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -1250,6 +1354,9 @@ static int launch_tc(const TcParams& p, int m_tiles, cudaStream_t stream) {
                                   : launch_tc_epi<BN, STAGES, 2>(p, m_tiles, stream);
     }
     if (p.epi5) return launch_tc_epi<BN, epi5_stages(BN, STAGES), 5>(p, m_tiles, stream);
+    if constexpr (BN >= 64) {
+        if (p.wide && p.store_mode == 1) return launch_tc_epi<BN, STAGES, 7>(p, m_tiles, stream);
+    }
     return p.direct ? launch_tc_epi<BN, STAGES, 3>(p, m_tiles, stream)
                     : launch_tc_epi<BN, STAGES, 1>(p, m_tiles, stream);
 }
@@ -1389,8 +1496,17 @@ static int gemm_tc(const svc_gemm_desc& d_in, cudaStream_t stream) {
         const bool res_inplace = d.res != nullptr && d.res == d.out_f32 && d.res_bstride == d.of_bstride &&
                                  d.res_rstride == d.of_rstride;
         if (d.out_op != nullptr && d.out_f32 == nullptr && d.res == nullptr && !d.accumulate) {
-            if (encode_out_map(&p.omap, d.out_op, false, p.epi.N_out, d.T, d.oo_rstride, d.B, d.oo_bstride, p.direct))
+            const bool pair_a = d.act == SVC_ACT_SWIGLU_PAIR || d.act == SVC_ACT_TANH_SIG_PAIR;
+#ifdef SVC_NO_WIDE_ITEMS
+            p.wide = 0;
+#else
+            p.wide = p.direct && !pair_a && BN >= 64 && d.row_ss_in == nullptr && d.N % 8 == 0;
+#endif
+            if (encode_out_map(&p.omap, d.out_op, false, p.epi.N_out, d.T, d.oo_rstride, d.B, d.oo_bstride, p.direct,
+                               p.wide ? 64 : 32))
                 p.store_mode = 1;
+            else
+                p.wide = 0;
         } else if (d.out_f32 != nullptr && d.out_op == nullptr && d.act != SVC_ACT_ROPE) {
             const bool add = (res_inplace && !d.accumulate && d.alpha == 1.0f) ||
                              (d.res == nullptr && d.accumulate);
