@@ -305,8 +305,9 @@ __device__ __forceinline__ uint32_t bf162_to_f162(uint32_t v) {
     return pack_f16(__low2float(p), __high2float(p));
 }
 
+// (64 registers per thread: 4 resident blocks of 256 threads, 5 of 192)
 template <typename TI, typename TO, int CT, int NS, int SPAN, bool SPLIT>
-__global__ void __launch_bounds__(32 * ((CT + 15) / 16) * NS)
+__global__ void __launch_bounds__(32 * ((CT + 15) / 16) * NS, 65536 / (64 * 32 * ((CT + 15) / 16) * NS))
 snake_mma_kernel(const TI* __restrict__ x, TO* __restrict__ out, const float* __restrict__ a_p,
                  const float* __restrict__ invb_p, int L, int C) {
     constexpr int MT = (CT + 15) / 16;          // 16-channel MMA row tiles per block
@@ -418,6 +419,8 @@ snake_mma_kernel(const TI* __restrict__ x, TO* __restrict__ out, const float* __
     const long long ostep = 8LL * C;
     const bool ovalid = mt * 16 + t * 4 < CT && c0 + mt * 16 + t * 4 < C;
 
+    const float2 a2_l = make_float2(a_l, a_l), ib2_l = make_float2(ib_l, ib_l);
+    const float2 a2_h = make_float2(a_h, a_h), ib2_h = make_float2(ib_h, ib_h);
     float vLl = 0.f, vLh = 0.f;                 // u[2L-1] of this thread's two channels, once seen
     uint32_t po[2], pe[2];                      // previous u tile, packed: [0] = channel g, [1] = channel g+8
 
@@ -436,10 +439,24 @@ snake_mma_kernel(const TI* __restrict__ x, TO* __restrict__ out, const float* __
             mma16816(uo, xa, bl[0][0], bl[0][1]);
             mma16816(ue, xa, bl[1][0], bl[1][1]);
         }
+#ifdef SVC_SNAKE_SCALAR
         uo[0] = snake_fn<false>(uo[0], a_l, ib_l); uo[1] = snake_fn<false>(uo[1], a_l, ib_l);
         uo[2] = snake_fn<false>(uo[2], a_h, ib_h); uo[3] = snake_fn<false>(uo[3], a_h, ib_h);
         ue[0] = snake_fn<false>(ue[0], a_l, ib_l); ue[1] = snake_fn<false>(ue[1], a_l, ib_l);
         ue[2] = snake_fn<false>(ue[2], a_h, ib_h); ue[3] = snake_fn<false>(ue[3], a_h, ib_h);
+#else
+        // packed f32x2 arithmetic around the two scalar sin.approx of a pair (both values of a pair belong to the
+        // same channel): 7 issue slots per pair instead of 10 - the loop is short of issue slots, not of pipe cycles
+        auto snake2 = [](float& x, float& y, float2 a2, float2 ib2) {
+            const float2 u = make_float2(x, y);
+            const float2 t = __fmul2_rn(u, a2);
+            const float2 sn = make_float2(__sinf(t.x), __sinf(t.y));
+            const float2 r = __ffma2_rn(__fmul2_rn(ib2, sn), sn, u);
+            x = r.x, y = r.y;
+        };
+        snake2(uo[0], uo[1], a2_l, ib2_l); snake2(uo[2], uo[3], a2_h, ib2_h);
+        snake2(ue[0], ue[1], a2_l, ib2_l); snake2(ue[2], ue[3], a2_h, ib2_h);
+#endif
         if constexpr (EDGE) {
             if (qs < 0 || qs + 8 >= L) {        // warp-uniform: frame 0 / frame L-1 or beyond inside this tile
                 if (qs < 0) {                   // q < 0 -> u[0] = ue[q = 0], column -qs
