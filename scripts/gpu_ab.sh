@@ -6,5 +6,5 @@ for lib in seed-vc_b200/libseedvc_b200_v_old.so seed-vc_b200/libseedvc_b200.so; 
  echo "== $lib"
  [ -n "$AB_VOC" ] && SEEDVC_B200_LIB=$PWD/$lib timeout 200 python scripts/voc_profile.py 2>&1 | tail -1
  [ -n "$AB_KB" ] && SEEDVC_B200_LIB=$PWD/$lib KB_FILTER="$AB_KB" timeout 200 python scripts/kbench.py gemm 2>&1 | head -4
- SEEDVC_B200_LIB=$PWD/$lib timeout 300 python scripts/dit_profile.py 2>&1 | grep -E "total per step|'rope,out_op'|, 2, 'out_op'|rowbias,out_op"
+ SEEDVC_B200_LIB=$PWD/$lib timeout 300 python scripts/dit_profile.py 2>&1 | grep -E "total per step|norm_mod|'rope,out_op'"
 done; done

@@ -19,9 +19,16 @@ __global__ void __launch_bounds__(256) norm_mod_kernel(
     const float* __restrict__ gamma, const float* __restrict__ mul, const float* __restrict__ add,
     float eps, int mode, TO* __restrict__ out, long long o_bstride, long long o_rstride, int B, int T,
     int D, TO* __restrict__ raw, int raw_f16) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int warp_lin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= B * T) return;
+    if (warp_lin >= B * T) return;
+#ifdef SVC_NORM_FORWARD
+    const int warp = warp_lin;
+#else
+    // rows from the END of the tensor first: the GEMM that produced x wrote it front to back, so its tail is what the
+    // 126 MB L2 still holds; and the rows written last here (the front) are the ones the next GEMM reads first
+    const int warp = B * T - 1 - warp_lin;
+#endif
     const int b = warp / T, t = warp % T;
     const float* xr = x + static_cast<long long>(b) * x_bstride + static_cast<long long>(t) * x_rstride;
     float4 v[MAXV];
